@@ -1,0 +1,211 @@
+// extern "C" entry points declared in include/ilqc_b200.h.  Shared by the product library (api.cu, nvcc)
+// and the test-only host simulator (tests/hostsim/api_hostsim.cpp).
+#include "launch.cuh"
+#include "solver.inl"
+
+namespace ilqc {
+int dense_lq_backward(int nx, int nu, int H, int B, int L, const double* A, const double* Bm, const double* p,
+                      const double* P, const double* q, const double* Q, const double* R, const double* reg_ctrl,
+                      double reg_state, double* K, double* k, double* jcst, stream_t st);
+int dense_rollout_lin(int nx, int nu, int H, int B, int L, const double* A, const double* Bm, const double* K,
+                      const double* k, const double* step, double* diff, stream_t st);
+}
+
+using namespace ilqc;
+
+extern "C" {
+
+int ilqc_abi_version(void) { return ILQC_ABI_VERSION; }
+
+int ilqc_dims(const ilqc_model_desc* m, int32_t* nx, int32_t* nu) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (nx) *nx = d.nx;
+  if (nu) *nu = d.nu;
+  return 0;
+}
+int ilqc_lin_stride(const ilqc_model_desc* m) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  return rc ? rc : d.lin_stride;
+}
+int ilqc_gain_stride(const ilqc_model_desc* m) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  return rc ? rc : d.gain_stride;
+}
+
+int ilqc_rollout_cost(const ilqc_model_desc* m, int B, const double* x0, const double* cmd, double* traj,
+                      double* cost_t, double* total, void* stream) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (B <= 0 || !x0 || !cmd) return ILQC_E_ARG;
+  ILQC_FOR_MODEL(m->model, return LM::forward(0, *m, B, x0, cmd, nullptr, traj, cost_t, total, nullptr, (stream_t)stream));
+  return 0;
+}
+
+int ilqc_linearize(const ilqc_model_desc* m, int B, const double* x0, const double* cmd, double* lin, double* traj,
+                   double* total, void* stream) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (B <= 0 || !x0 || !cmd || !lin) return ILQC_E_ARG;
+  ILQC_FOR_MODEL(m->model, return LM::forward(1, *m, B, x0, cmd, lin, traj, nullptr, total, nullptr, (stream_t)stream));
+  return 0;
+}
+
+int ilqc_expand_dense(const ilqc_model_desc* m, int B, const double* x0, const double* cmd, int order, double* A,
+                      double* Bm, double* p, double* P, double* q, double* Q, const double* lam, double* Hxx,
+                      double* Hxu, double* Huu, void* stream) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (B <= 0 || !x0 || !cmd || !A || !Bm || !p || !P || !q || !Q) return ILQC_E_ARG;
+  if (order >= 2 && (!lam || !Hxx || !Hxu || !Huu)) return ILQC_E_ARG;
+  ILQC_FOR_MODEL(m->model, return LM::expand_dense(*m, B, x0, cmd, order, A, Bm, p, P, q, Q, lam, Hxx, Hxu, Huu,
+                                                   (stream_t)stream));
+  return 0;
+}
+
+int ilqc_lq_backward_dense(int nx, int nu, int H, int B, int L, const double* A, const double* Bm, const double* p,
+                           const double* P, const double* q, const double* Q, const double* R,
+                           const double* reg_ctrl, double reg_state, double* K, double* k, double* jcst,
+                           void* stream) {
+  if (H <= 0 || B <= 0 || L <= 0 || !A || !Bm || !p || !P || !q || !Q || !reg_ctrl || !K || !k || !jcst)
+    return ILQC_E_ARG;
+  return dense_lq_backward(nx, nu, H, B, L, A, Bm, p, P, q, Q, R, reg_ctrl, reg_state, K, k, jcst, (stream_t)stream);
+}
+
+int ilqc_rollout_lin_dense(int nx, int nu, int H, int B, int L, const double* A, const double* Bm, const double* K,
+                           const double* k, const double* step, double* diff, void* stream) {
+  if (H <= 0 || B <= 0 || L <= 0 || !A || !Bm || !K || !k || !step || !diff) return ILQC_E_ARG;
+  return dense_rollout_lin(nx, nu, H, B, L, A, Bm, K, k, step, diff, (stream_t)stream);
+}
+
+int ilqc_backward(const ilqc_model_desc* m, int mode, int B, int n_slots, const int32_t* prob,
+                  const double* reg_ctrl, double reg_state, const double* lin, const double* traj,
+                  const double* cmd, double* gains, double* jcst, int32_t* feasible, void* stream) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (B <= 0 || n_slots <= 0 || !reg_ctrl || !lin || !gains || !jcst) return ILQC_E_ARG;
+  if (mode != ILQC_BWD_LINQUAD && (!traj || !cmd)) return ILQC_E_ARG;
+  ILQC_FOR_MODEL(m->model, return LM::backward(mode, *m, B, n_slots, prob, nullptr, n_slots, reg_ctrl, reg_state, lin,
+                                               traj, cmd, gains, jcst, feasible, (stream_t)stream));
+  return 0;
+}
+
+int ilqc_rollout(const ilqc_model_desc* m, int kind, int B, int n_slots, const int32_t* prob, const int32_t* gslot,
+                 const double* step, const double* x0, const double* cmd, const double* traj, const double* lin,
+                 const double* gains, const double* grad, double* diff, double* newval, double* diffsq,
+                 void* stream) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (B <= 0 || n_slots <= 0 || !step || !x0 || !cmd || !diff || !newval || !diffsq) return ILQC_E_ARG;
+  if (kind == ILQC_ROLL_EXACT && (!traj || !gains)) return ILQC_E_ARG;
+  if (kind == ILQC_ROLL_LIN && (!lin || !gains)) return ILQC_E_ARG;
+  if (kind == ILQC_ROLL_GD && !grad) return ILQC_E_ARG;
+  ILQC_FOR_MODEL(m->model, return LM::rollout(kind, *m, B, n_slots, prob, gslot, n_slots, nullptr, n_slots, step, x0, cmd,
+                                              traj, lin, gains, grad, diff, newval, diffsq, (stream_t)stream));
+  return 0;
+}
+
+int ilqc_grad_obj(const ilqc_model_desc* m, int B, const double* lin, double* grad, double* gnorm, double* cnorm,
+                  void* stream) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (B <= 0 || !lin || !gnorm) return ILQC_E_ARG;
+  (void)cnorm;
+  ILQC_FOR_MODEL(m->model, return LM::adjoint(*m, B, lin, grad, gnorm, (stream_t)stream));
+  return 0;
+}
+
+size_t ilqc_solve_workspace_bytes(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B) {
+  Dims d;
+  if (get_dims(m, &d) || !a || B <= 0 || a->n_candidates < 1) return 0;
+  Workspace w;
+  carve(&w, nullptr, d, m->horizon, B, a->n_candidates);
+  return w.bytes;
+}
+
+int ilqc_solve(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const double* x0, double* cmd,
+               double* stepsize, int n_iter, double* cost, double* gnorm, double* step_rep, int32_t* n_done,
+               int32_t* status, int32_t* ls_trips, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!m || !a || !x0 || !cmd || !stepsize || !cost || !gnorm || !step_rep || !n_done || !status) return ILQC_E_ARG;
+  return solve_impl(m, a, B, x0, cmd, stepsize, n_iter, cost, gnorm, step_rep, n_done, status, ls_trips, workspace,
+                    workspace_bytes, (stream_t)stream);
+}
+
+int ilqc_to_soa(const double* src, double* dst, int B, int n, void* stream) {
+  if (!src || !dst || B <= 0 || n <= 0) return ILQC_E_ARG;
+  ILQC_LAUNCH((to_soa_kernel), B * n, 256, (stream_t)stream, src, dst, B, n);
+  return ILQC_LAUNCH_OK();
+}
+int ilqc_from_soa(const double* src, double* dst, int B, int n, void* stream) {
+  if (!src || !dst || B <= 0 || n <= 0) return ILQC_E_ARG;
+  ILQC_LAUNCH((from_soa_kernel), B * n, 256, (stream_t)stream, src, dst, B, n);
+  return ILQC_LAUNCH_OK();
+}
+
+// ---- host-buffer entry point ---------------------------------------------------------------------------
+// device staging: x0 [B][nx] + cmd [B][H][nu] + stepsize + metrics (3 x [n_iter+1][B]) in both layouts
+static size_t host_stage_doubles(const Dims& d, int H, int B, int n_iter) {
+  return (size_t)B * d.nx * 2 + (size_t)B * H * d.nu * 2 + (size_t)B + (size_t)3 * (n_iter + 1) * B * 2;
+}
+size_t ilqc_solve_host_workspace_bytes(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, int n_iter) {
+  Dims d;
+  if (get_dims(m, &d) || !a || B <= 0) return 0;
+  const size_t ws = ilqc_solve_workspace_bytes(m, a, B);
+  return ws + align_up(host_stage_doubles(d, m->horizon, B, n_iter) * sizeof(double)) + align_up((size_t)2 * B * 4) + 512;
+}
+int ilqc_solve_host(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const double* x0_host, double* cmd_host,
+                    double* stepsize_host, int n_iter, double* cost_host, double* gnorm_host, double* step_rep_host,
+                    int32_t* n_done_host, int32_t* status_host, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (!a || B <= 0 || !x0_host || !cmd_host || !stepsize_host || !cost_host || !status_host) return ILQC_E_ARG;
+  if (workspace_bytes < ilqc_solve_host_workspace_bytes(m, a, B, n_iter)) return ILQC_E_WORKSPACE;
+  const int H = m->horizon;
+  stream_t st = (stream_t)stream;
+  const size_t ws = align_up(ilqc_solve_workspace_bytes(m, a, B));
+  char* base = (char*)workspace + ws;
+  double* x0_aos = (double*)base;
+  double* x0_soa = x0_aos + (size_t)B * d.nx;
+  double* cmd_aos = x0_soa + (size_t)B * d.nx;
+  double* cmd_soa = cmd_aos + (size_t)B * H * d.nu;
+  double* step_d = cmd_soa + (size_t)B * H * d.nu;
+  const size_t mrows = (size_t)(n_iter + 1) * B;
+  double* met_soa = step_d + B;      // cost, gnorm, step_rep  [n_iter+1][B]
+  double* met_aos = met_soa + 3 * mrows;  // [B][n_iter+1]
+  int32_t* ints = (int32_t*)(base + align_up(host_stage_doubles(d, H, B, n_iter) * sizeof(double)));
+  int32_t* n_done_d = ints;
+  int32_t* status_d = ints + B;
+#define ILQC_CHECK(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+  ILQC_CHECK(dev_h2d(x0_aos, x0_host, sizeof(double) * B * d.nx, st));
+  ILQC_CHECK(dev_h2d(cmd_aos, cmd_host, sizeof(double) * B * H * d.nu, st));
+  ILQC_CHECK(dev_h2d(step_d, stepsize_host, sizeof(double) * B, st));
+  ILQC_CHECK(ilqc_to_soa(x0_aos, x0_soa, B, d.nx, stream));
+  ILQC_CHECK(ilqc_to_soa(cmd_aos, cmd_soa, B, H * d.nu, stream));
+  ILQC_CHECK(solve_impl(m, a, B, x0_soa, cmd_soa, step_d, n_iter, met_soa, met_soa + mrows, met_soa + 2 * mrows,
+                        n_done_d, status_d, nullptr, workspace, ws, st));
+  ILQC_CHECK(ilqc_from_soa(cmd_soa, cmd_aos, B, H * d.nu, stream));
+  for (int k = 0; k < 3; ++k) ILQC_CHECK(ilqc_from_soa(met_soa + k * mrows, met_aos + k * mrows, B, n_iter + 1, stream));
+  ILQC_CHECK(dev_d2h(cmd_host, cmd_aos, sizeof(double) * B * H * d.nu, st));
+  ILQC_CHECK(dev_d2h(stepsize_host, step_d, sizeof(double) * B, st));
+  ILQC_CHECK(dev_d2h(cost_host, met_aos, sizeof(double) * mrows, st));
+  if (gnorm_host) ILQC_CHECK(dev_d2h(gnorm_host, met_aos + mrows, sizeof(double) * mrows, st));
+  if (step_rep_host) ILQC_CHECK(dev_d2h(step_rep_host, met_aos + 2 * mrows, sizeof(double) * mrows, st));
+  if (n_done_host) ILQC_CHECK(dev_d2h(n_done_host, n_done_d, sizeof(int32_t) * B, st));
+  ILQC_CHECK(dev_d2h(status_host, status_d, sizeof(int32_t) * B, st));
+  ILQC_CHECK(dev_sync(st));
+#undef ILQC_CHECK
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,442 @@
+// Per-slot bodies of the hot-path kernels (one CUDA thread = one problem or one (problem, candidate)).
+// HBM layout everywhere: [time][component][slot] with the slot (batch) index innermost, so a warp reads
+// 32 consecutive doubles per component (fully coalesced 256 B requests).
+//
+// Reference functions restated (file:line in /root/reference):
+//   forward_body   DiffEnv.forward/step, diff_discrete_dyn, diff_cost      envs/forward.py:62-139, :188-321
+//   backward_body  lin_quad_backward, quad_backward(_ddp/_newton)          envs/backward.py:6-150
+//   rollout_body   roll_out_exact, roll_out_lin, gd direction + obj(...)   envs/rollout.py:8-88,
+//                                                                          algorithms/algos_steps.py:22-43, :329-331
+//   adjoint_body   torch.autograd.grad(sum(costs), cmd)                    algorithms/run_min_algo.py:156-157
+#pragma once
+#include "common.cuh"
+#include "jet.cuh"
+#include "models.cuh"
+#include "riccati.cuh"
+
+namespace ilqc {
+
+// ----------------------------------------------------------------------------------------------------
+// expansion of one step: fills the packed record `rec` (Layout<M>) for step t from (x_t, u_t) and
+// returns x_{t+1}, the step cost and |grad_ctrl|^2+|grad_state|^2 (algos_steps.py:342-351)
+// ----------------------------------------------------------------------------------------------------
+template <class M, class Store>
+ILQC_HD void expand_step(const ilqc_model_desc& m, const Weights& w, const double (&x)[M::NX],
+                         const double (&u)[M::NU], int time_next, double (&xn)[M::NX], double* cost,
+                         double* gsq, Store&& store) {
+  using L = Layout<M>;
+  constexpr int NX = M::NX, NU = M::NU;
+  {
+    using S = Jet<M::NV, 1>;
+    S xs[NX], us[NU], xns[NX];
+    static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], M::sv(I)); });
+    static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], M::uv(I)); });
+    M::template step<S>(m, xs, us, xns);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xn[i] = xns[i].v;
+    // N = A - I, B
+    static_for<NX>([&](auto I) {
+      constexpr int i = I;
+      static_for<NX>([&](auto Jc) {
+        constexpr int j = Jc;
+        if constexpr (M::Nm(i, j)) {
+          double v;
+          if constexpr (M::sv(j) >= 0) v = xns[i].g[M::sv(j)] - (i == j ? 1.0 : 0.0);
+          else v = passive_N_of<M>(m, i, j);
+          store(L::oN + M::Nm.slot(i, j), v);
+        }
+      });
+      static_for<NU>([&](auto Kc) {
+        constexpr int k = Kc;
+        if constexpr (M::Bm(i, k)) {
+          double v;
+          if constexpr (M::uv(k) >= 0) v = xns[i].g[M::uv(k)];
+          else v = passive_B_of<M>(m, i, k);
+          store(L::oB + M::Bm.slot(i, k), v);
+        }
+      });
+    });
+  }
+  double gs = 0.0;
+  {
+    double q[NU], Qd[NU];
+    const double cc = M::ctrl_cost(m, u, q, Qd);
+    double gc = 0.0;
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      store(L::oq + i, q[i]);
+      store(L::oQ + i, Qd[i]);
+      gc += q[i] * q[i];
+    }
+    using SC = Jet<M::NVC, 2>;
+    SC xc[NX];
+    static_for<NX>([&](auto I) { xc[I] = make_var<SC>(xn[I], M::cv(I)); });
+    const SC c = M::template state_cost<SC>(m, w, xc, time_next);
+    static_for<NX>([&](auto I) {
+      constexpr int i = I;
+      if constexpr (M::pm(0, i)) {
+        const double v = c.g[M::cv(i)];
+        store(L::op + M::pm.slot(0, i), v);
+        gs += v * v;
+      }
+      static_for<NX>([&](auto Jc) {
+        constexpr int j = Jc;
+        if constexpr (j >= i && M::Pm(i, j)) store(L::oP + M::Pm.slot(i, j), c.h[sym_idx(M::cv(i), M::cv(j), M::NVC)]);
+      });
+    });
+    *cost = c.v + cc;
+    *gsq = gc + gs;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// forward: ORD==0 roll-out + costs ; ORD==1 additionally the packed expansion
+// ----------------------------------------------------------------------------------------------------
+template <class M, int ORD>
+ILQC_HD void forward_body(const ilqc_model_desc& m, int b, int B, const double* __restrict__ x0,
+                          const double* __restrict__ cmd, double* __restrict__ lin, double* __restrict__ traj,
+                          double* __restrict__ cost_t, double* __restrict__ total, double* __restrict__ cnorm) {
+  constexpr int NX = M::NX, NU = M::NU;
+  const int H = m.horizon;
+  const Weights w = load_weights(m, b, B);
+  const int t0 = load_t0(m, b);
+  double x[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    x[i] = x0[(size_t)i * B + b];
+    if (traj) traj[(size_t)i * B + b] = x[i];
+  }
+  if (cost_t) cost_t[b] = 0.0;
+  double tot = 0.0, gsum = 0.0;
+  for (int t = 0; t < H; ++t) {
+    double u[NU], xn[NX], c;
+#pragma unroll
+    for (int k = 0; k < NU; ++k) u[k] = cmd[((size_t)t * NU + k) * B + b];
+    if constexpr (ORD == 0) {
+      M::template step<double>(m, x, u, xn);
+      double q[NU], Qd[NU];
+      const double cs = M::template state_cost<double>(m, w, xn, t0 + t + 1);
+      c = cs + M::ctrl_cost(m, u, q, Qd);
+    } else {
+      double gsq;
+      double* rec = lin + (size_t)t * Layout<M>::stride * B + b;
+      expand_step<M>(m, w, x, u, t0 + t + 1, xn, &c, &gsq, [&](int slot, double v) { rec[(size_t)slot * B] = v; });
+      gsum += gsq;
+    }
+    tot = tot + c;
+    if (cost_t) cost_t[(size_t)(t + 1) * B + b] = c;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      x[i] = xn[i];
+      if (traj) traj[((size_t)(t + 1) * NX + i) * B + b] = xn[i];
+    }
+  }
+  if (total) total[b] = tot;
+  if (cnorm) cnorm[b] = ::sqrt(gsum);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// loads of the packed record into the Riccati operands
+// ----------------------------------------------------------------------------------------------------
+template <class M, class BellT>
+ILQC_HD void load_dyn(BellT& bl, const double* __restrict__ rec, int B) {
+  using L = Layout<M>;
+  static_for<M::NX>([&](auto I) {
+    constexpr int i = I;
+    static_for<M::NX>([&](auto Jc) {
+      constexpr int j = Jc;
+      if constexpr (M::Nm(i, j)) bl.N[i][j] = rec[(size_t)(L::oN + M::Nm.slot(i, j)) * B];
+    });
+    static_for<M::NU>([&](auto Kc) {
+      constexpr int k = Kc;
+      if constexpr (M::Bm(i, k)) bl.B[i][k] = rec[(size_t)(L::oB + M::Bm.slot(i, k)) * B];
+    });
+  });
+}
+template <class M>
+ILQC_HD void load_state_cost(double (&p)[M::NX], double (&P)[M::NX][M::NX], const double* __restrict__ rec, int B) {
+  using L = Layout<M>;
+  static_for<M::NX>([&](auto I) {
+    constexpr int i = I;
+    if constexpr (M::pm(0, i)) p[i] = rec[(size_t)(L::op + M::pm.slot(0, i)) * B]; else p[i] = 0.0;
+    static_for<M::NX>([&](auto Jc) {
+      constexpr int j = Jc;
+      if constexpr (j >= i) {
+        if constexpr (M::Pm(i, j)) P[i][j] = rec[(size_t)(L::oP + M::Pm.slot(i, j)) * B]; else P[i][j] = 0.0;
+      }
+    });
+  });
+}
+
+// ----------------------------------------------------------------------------------------------------
+// backward pass (MODE = ILQC_BWD_*).  slot s serves problem b with regularisation reg_ctrl.
+// gains record per step: [K row-major NU x NX | k NU], layout [t][gain_stride][n_slots]
+// ----------------------------------------------------------------------------------------------------
+template <class M, int MODE>
+ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, int B, double reg_ctrl,
+                           double reg_state, const double* __restrict__ lin, const double* __restrict__ traj,
+                           const double* __restrict__ cmd, double* __restrict__ gains,
+                           double* __restrict__ jcst_out, int32_t* __restrict__ feas_out) {
+  constexpr int NX = M::NX, NU = M::NU;
+  constexpr bool QUAD = (MODE != ILQC_BWD_LINQUAD);
+  using L = Layout<M>;
+  using Pat = PatOf<M, QUAD>;
+  const int H = m.horizon;
+  Bell<Pat> bl;
+  double J[sym_size(NX)], j[NX];
+  {
+    double pH[NX], PH[NX][NX];
+    load_state_cost<M>(pH, PH, lin + (size_t)(H - 1) * L::stride * B + b, B);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      j[i] = pH[i];
+#pragma unroll
+      for (int c = i; c < NX; ++c) J[sym_idx(i, c, NX)] = PH[i][c] + (i == c ? reg_state : 0.0);
+    }
+  }
+  double lam[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) lam[i] = j[i];
+  double jcst = 0.0;
+  for (int t = H - 1; t >= 0; --t) {
+    const double* rec = lin + (size_t)t * L::stride * B + b;
+    load_dyn<M>(bl, rec, B);
+    double pc[NX], Pc[NX][NX];
+    if (t > 0) {
+      load_state_cost<M>(pc, Pc, lin + (size_t)(t - 1) * L::stride * B + b, B);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        pc[i] = 0.0;
+#pragma unroll
+        for (int c = i; c < NX; ++c) Pc[i][c] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      bl.p[i] = pc[i];
+#pragma unroll
+      for (int c = i; c < NX; ++c) bl.P[i][c] = Pc[i][c];
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      bl.q[u] = rec[(size_t)(L::oq + u) * B];
+#pragma unroll
+      for (int v = u; v < NU; ++v) bl.Q[u][v] = 0.0;
+      bl.Q[u][u] = rec[(size_t)(L::oQ + u) * B] + reg_ctrl;
+    }
+    if constexpr (!QUAD) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) bl.P[i][i] += reg_state;
+    } else {
+      // Hessian of lam^T phi at (x_t, u_t) (forward.py:218-269) by second-order jets
+      using S = Jet<M::NV, 2>;
+      double x[NX], u[NU];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = traj[((size_t)t * NX + i) * B + b];
+#pragma unroll
+      for (int k = 0; k < NU; ++k) u[k] = cmd[((size_t)t * NU + k) * B + b];
+      S xs[NX], us[NU], xns[NX];
+      static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], M::sv(I)); });
+      static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], M::uv(I)); });
+      M::template step<S>(m, xs, us, xns);
+      double hl[sym_size(M::NV)];
+#pragma unroll
+      for (int e = 0; e < sym_size(M::NV); ++e) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) acc += lam[i] * xns[i].h[e];
+        hl[e] = acc;
+      }
+      static_for<NX>([&](auto I) {
+        constexpr int i = I;
+        if constexpr (M::sv(i) >= 0) {
+          static_for<NX>([&](auto Jc) {
+            constexpr int c = Jc;
+            if constexpr (c >= i && M::sv(c) >= 0) {
+              // P gets the state block only for t>0 (backward.py:102-108)
+              if (t > 0) bl.P[i][c] += hl[sym_idx(M::sv(i), M::sv(c), M::NV)];
+            }
+          });
+          static_for<NU>([&](auto Kc) {
+            constexpr int k = Kc;
+            if constexpr (M::uv(k) >= 0) bl.R[i][k] = hl[sym_idx(M::sv(i), M::uv(k), M::NV)];
+          });
+        }
+      });
+      static_for<NU>([&](auto U) {
+        constexpr int u1 = U;
+        if constexpr (M::uv(u1) >= 0) {
+          static_for<NU>([&](auto V) {
+            constexpr int v1 = V;
+            if constexpr (v1 >= u1 && M::uv(v1) >= 0) bl.Q[u1][v1] += hl[sym_idx(M::uv(u1), M::uv(v1), M::NV)];
+          });
+        }
+      });
+      if (t > 0) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) bl.P[i][i] += reg_state;
+      }
+    }
+    // newton-mode costate uses j-independent recursion lam <- p + A^T lam (backward.py:122-123)
+    double lam_next[NX];
+    if constexpr (MODE == ILQC_BWD_QUAD_NEWTON) {
+      static_for<NX>([&](auto I) {
+        constexpr int i = I;
+        double acc = pc[i] + lam[i];
+        static_for<NX>([&](auto Rr) {
+          constexpr int r = Rr;
+          if constexpr (M::Nm(r, i)) acc += bl.N[r][i] * lam[r];
+        });
+        lam_next[i] = acc;
+      });
+    }
+    const double rest = bl.step(J, j);
+    jcst = jcst + rest;
+    double* g = gains + (size_t)t * L::gain_stride * n_slots + s;
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+#pragma unroll
+      for (int c = 0; c < NX; ++c) g[(size_t)(u * NX + c) * n_slots] = bl.K[u][c];
+      g[(size_t)(NU * NX + u) * n_slots] = bl.k[u];
+    }
+    if constexpr (MODE == ILQC_BWD_QUAD_NEWTON) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) lam[i] = lam_next[i];
+    } else if constexpr (MODE == ILQC_BWD_QUAD_DDP) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) lam[i] = j[i];
+    }
+  }
+  jcst_out[s] = jcst;
+  // handle_bad_dir == 'check_total_value' (run_min_algo.py:21): linquad is always feasible,
+  // the quad variants require a negative model decrease (backward.py:130-131)
+  if (feas_out) feas_out[s] = QUAD ? (jcst < 0.0 ? 1 : 0) : 1;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// roll-outs fused with the objective of the candidate.
+//   EXACT: v_t = K_t (x_t - xbar_t) + step*k_t along the true dynamics              (rollout.py:50-88)
+//   LIN  : v_t = K_t dx_t + step*k_t ; dx_{t+1} = A_t dx_t + B_t v_t                (rollout.py:8-47)
+//   DIR  : v_t = step * dir_t   (classic 'dir' oracles and gd, algos_steps.py:38-41, :153-160)
+// In every case newval = sum of costs along the true dynamics under cmd+v (algos_steps.py:329-331).
+// ----------------------------------------------------------------------------------------------------
+template <class M, int KIND>
+ILQC_HD void rollout_body(const ilqc_model_desc& m, int s, int n_slots, int b, int B, int gs, int n_gslots,
+                          double step, const double* __restrict__ x0, const double* __restrict__ cmd,
+                          const double* __restrict__ traj, const double* __restrict__ lin,
+                          const double* __restrict__ gains, const double* __restrict__ dir,
+                          double* __restrict__ diff, double* __restrict__ newval, double* __restrict__ diffsq) {
+  constexpr int NX = M::NX, NU = M::NU;
+  using L = Layout<M>;
+  const int H = m.horizon;
+  const Weights w = load_weights(m, b, B);
+  const int t0 = load_t0(m, b);
+  double x[NX], dx[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    x[i] = x0[(size_t)i * B + b];
+    dx[i] = 0.0;
+  }
+  double tot = 0.0, nsq = 0.0;
+  for (int t = 0; t < H; ++t) {
+    double v[NU], u[NU];
+    if constexpr (KIND == ILQC_ROLL_GD) {
+#pragma unroll
+      for (int k = 0; k < NU; ++k) v[k] = step * dir[((size_t)t * NU + k) * B + b];
+    } else {
+      const double* g = gains + (size_t)t * L::gain_stride * n_gslots + gs;
+#pragma unroll
+      for (int k = 0; k < NU; ++k) {
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < NX; ++c) acc += g[(size_t)(k * NX + c) * n_gslots] * dx[c];
+        v[k] = acc + step * g[(size_t)(NU * NX + k) * n_gslots];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NU; ++k) {
+      diff[((size_t)t * NU + k) * n_slots + s] = v[k];
+      nsq += v[k] * v[k];
+      u[k] = cmd[((size_t)t * NU + k) * B + b] + v[k];
+    }
+    if constexpr (KIND == ILQC_ROLL_LIN) {
+      // dx <- A dx + B v = dx + N dx + B v on the packed expansion
+      const double* rec = lin + (size_t)t * L::stride * B + b;
+      double dn[NX];
+      static_for<NX>([&](auto I) {
+        constexpr int i = I;
+        double acc = dx[i];
+        static_for<NX>([&](auto Jc) {
+          constexpr int c = Jc;
+          if constexpr (M::Nm(i, c)) acc += rec[(size_t)(L::oN + M::Nm.slot(i, c)) * B] * dx[c];
+        });
+        static_for<NU>([&](auto Kc) {
+          constexpr int k = Kc;
+          if constexpr (M::Bm(i, k)) acc += rec[(size_t)(L::oB + M::Bm.slot(i, k)) * B] * v[k];
+        });
+        dn[i] = acc;
+      });
+#pragma unroll
+      for (int i = 0; i < NX; ++i) dx[i] = dn[i];
+    }
+    double xn[NX], q[NU], Qd[NU];
+    M::template step<double>(m, x, u, xn);
+    const double cs = M::template state_cost<double>(m, w, xn, t0 + t + 1);
+    const double c = cs + M::ctrl_cost(m, u, q, Qd);
+    tot = tot + c;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      x[i] = xn[i];
+      if constexpr (KIND == ILQC_ROLL_EXACT) dx[i] = xn[i] - traj[((size_t)(t + 1) * NX + i) * B + b];
+    }
+  }
+  newval[s] = tot;
+  diffsq[s] = nsq;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// gradient of the total cost wrt the controls by the adjoint recursion on the packed expansion
+// ----------------------------------------------------------------------------------------------------
+template <class M>
+ILQC_HD void adjoint_body(const ilqc_model_desc& m, int b, int B, const double* __restrict__ lin,
+                          double* __restrict__ grad, double* __restrict__ gnorm) {
+  constexpr int NX = M::NX, NU = M::NU;
+  using L = Layout<M>;
+  const int H = m.horizon;
+  double carry[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) carry[i] = 0.0;
+  double nsq = 0.0;
+  for (int t = H - 1; t >= 0; --t) {
+    const double* rec = lin + (size_t)t * L::stride * B + b;
+    double lam[NX];
+    static_for<NX>([&](auto I) {
+      constexpr int i = I;
+      lam[i] = carry[i];
+      if constexpr (M::pm(0, i)) lam[i] += rec[(size_t)(L::op + M::pm.slot(0, i)) * B];
+    });
+    static_for<NU>([&](auto Kc) {
+      constexpr int k = Kc;
+      double acc = rec[(size_t)(L::oq + k) * B];
+      static_for<NX>([&](auto I) {
+        constexpr int i = I;
+        if constexpr (M::Bm(i, k)) acc += rec[(size_t)(L::oB + M::Bm.slot(i, k)) * B] * lam[i];
+      });
+      if (grad) grad[((size_t)t * NU + k) * B + b] = acc;
+      nsq += acc * acc;
+    });
+    static_for<NX>([&](auto I) {
+      constexpr int i = I;
+      double acc = lam[i];
+      static_for<NX>([&](auto Rr) {
+        constexpr int r = Rr;
+        if constexpr (M::Nm(r, i)) acc += rec[(size_t)(L::oN + M::Nm.slot(r, i)) * B] * lam[r];
+      });
+      carry[i] = acc;
+    });
+  }
+  gnorm[b] = ::sqrt(nsq);
+}
+
+}  // namespace ilqc

@@ -1,0 +1,77 @@
+// Launch plumbing shared by all translation units.
+//
+// Product build (nvcc, sm_100a): ILQC_LAUNCH enqueues a __global__ kernel, one thread per slot, on the
+// caller's stream.  Test-only build (-DILQC_HOSTSIM, g++): the same "kernel" functions are called in a
+// loop on the CPU so that the container without a GPU can check the arithmetic against the golden
+// vectors (tests/hostsim).  The host simulator is never part of libilqc_b200.so.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include "common.cuh"
+#include "../../include/ilqc_b200.h"
+
+#if defined(ILQC_HOSTSIM)
+namespace ilqc {
+extern thread_local int g_sim_tid;
+typedef void* stream_t;
+}
+#define ILQC_GLOBAL static void
+#define ILQC_TID (::ilqc::g_sim_tid)
+#define ILQC_UNPAREN(...) __VA_ARGS__
+#define ILQC_LAUNCH(kern, n, block, stream, ...)                 \
+  do {                                                           \
+    for (int _i = 0; _i < (int)(n); ++_i) {                      \
+      ::ilqc::g_sim_tid = _i;                                    \
+      ILQC_UNPAREN kern(__VA_ARGS__);                            \
+    }                                                            \
+  } while (0)
+#define ILQC_LAUNCH_OK() 0
+#else
+#include <cuda_runtime.h>
+namespace ilqc {
+typedef cudaStream_t stream_t;
+}
+#define ILQC_GLOBAL __global__ void
+#define ILQC_TID ((int)(blockIdx.x * blockDim.x + threadIdx.x))
+#define ILQC_UNPAREN(...) __VA_ARGS__
+#define ILQC_LAUNCH(kern, n, block, stream, ...)                                                   \
+  do {                                                                                             \
+    if ((n) > 0) ILQC_UNPAREN kern<<<((n) + (block)-1) / (block), (block), 0, (stream)>>>(__VA_ARGS__); \
+  } while (0)
+#define ILQC_LAUNCH_OK() ((int)cudaGetLastError())
+#endif
+
+namespace ilqc {
+
+// thread-block size of the thread-per-problem kernels.  The big bodies use ~255 registers, so an SM holds
+// 256 threads; small blocks keep all 148 SMs busy for batches that are not a multiple of 148*256.
+constexpr int kBlock = 64;
+
+// Per-model launchers, defined once per model in model_kernels.inl (one translation unit per model so
+// that the heavy templates compile in parallel).
+template <int MODEL>
+struct Launch {
+  static int forward(int order, const ilqc_model_desc& m, int B, const double* x0, const double* cmd,
+                     double* lin, double* traj, double* cost_t, double* total, double* cnorm, stream_t st);
+  static int expand_dense(const ilqc_model_desc& m, int B, const double* x0, const double* cmd, int order,
+                          double* A, double* Bm, double* p, double* P, double* q, double* Q, const double* lam,
+                          double* Hxx, double* Hxu, double* Huu, stream_t st);
+  // n_threads threads; thread s serves problem prob[s] (NULL: s) and reads/writes the per-slot arrays
+  // (reg_ctrl, gains, jcst, feasible / diff, newval, diffsq) at index oslot[s] (NULL: s) with slot
+  // stride n_oslots; roll-outs read their gains at gslot[s] (NULL: s) with stride n_gslots.
+  static int backward(int mode, const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob,
+                      const int32_t* oslot, int n_oslots, const double* reg_ctrl, double reg_state,
+                      const double* lin, const double* traj, const double* cmd, double* gains, double* jcst,
+                      int32_t* feasible, stream_t st);
+  static int rollout(int kind, const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob,
+                     const int32_t* gslot, int n_gslots, const int32_t* oslot, int n_oslots, const double* step,
+                     const double* x0, const double* cmd, const double* traj, const double* lin,
+                     const double* gains, const double* dir, double* diff, double* newval, double* diffsq,
+                     stream_t st);
+  static int adjoint(const ilqc_model_desc& m, int B, const double* lin, double* grad, double* gnorm,
+                     stream_t st);
+  static void dims(int* nx, int* nu, int* lin_stride, int* gain_stride);
+};
+
+}  // namespace ilqc

@@ -1,0 +1,222 @@
+// Kernels + launchers of ONE model (ILQC_MODEL_INST), included by model_<k>.cu (product, nvcc) and by
+// the test-only host simulator.  Each kernel is a thread-per-slot wrapper around a body of bodies.cuh.
+#include "launch.cuh"
+#include "bodies.cuh"
+
+#ifndef ILQC_MODEL_INST
+#error "define ILQC_MODEL_INST"
+#endif
+
+namespace ilqc {
+
+namespace {
+using MI = Model<ILQC_MODEL_INST>;
+
+template <class M, int ORD>
+ILQC_GLOBAL forward_kernel(ilqc_model_desc m, int B, const double* x0, const double* cmd, double* lin,
+                           double* traj, double* cost_t, double* total, double* cnorm) {
+  const int b = ILQC_TID;
+  if (b >= B) return;
+  forward_body<M, ORD>(m, b, B, x0, cmd, lin, traj, cost_t, total, cnorm);
+}
+
+template <class M, int MODE>
+ILQC_GLOBAL backward_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const int32_t* oslot,
+                            int n_oslots, const double* reg_ctrl, double reg_state, const double* lin,
+                            const double* traj, const double* cmd, double* gains, double* jcst, int32_t* feasible) {
+  const int s = ILQC_TID;
+  if (s >= n_threads) return;
+  const int b = prob ? prob[s] : s;
+  const int os = oslot ? oslot[s] : s;
+  backward_body<M, MODE>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, gains, jcst, feasible);
+}
+
+template <class M, int KIND>
+ILQC_GLOBAL rollout_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const int32_t* gslot,
+                           int n_gslots, const int32_t* oslot, int n_oslots, const double* step, const double* x0,
+                           const double* cmd, const double* traj, const double* lin, const double* gains,
+                           const double* dir, double* diff, double* newval, double* diffsq) {
+  const int s = ILQC_TID;
+  if (s >= n_threads) return;
+  const int b = prob ? prob[s] : s;
+  const int gs = gslot ? gslot[s] : s;
+  const int os = oslot ? oslot[s] : s;
+  rollout_body<M, KIND>(m, os, n_oslots, b, B, gs, n_gslots, step[s], x0, cmd, traj, lin, gains, dir, diff, newval,
+                        diffsq);
+}
+
+template <class M>
+ILQC_GLOBAL adjoint_kernel(ilqc_model_desc m, int B, const double* lin, double* grad, double* gnorm) {
+  const int b = ILQC_TID;
+  if (b >= B) return;
+  adjoint_body<M>(m, b, B, lin, grad, gnorm);
+}
+
+// Dense dump of the expansion in the reference's own shapes (forward.py:209-216, :299-319) and of the
+// dynamics-Hessian closures at given lambdas (forward.py:218-269).  Test / interop path, not tuned.
+template <class M>
+ILQC_GLOBAL expand_dense_kernel(ilqc_model_desc m, int B, const double* x0, const double* cmd, int order,
+                                double* A, double* Bm, double* p, double* P, double* q, double* Q,
+                                const double* lam, double* Hxx, double* Hxu, double* Huu) {
+  const int b = ILQC_TID;
+  if (b >= B) return;
+  constexpr int NX = M::NX, NU = M::NU;
+  using L = Layout<M>;
+  const int H = m.horizon;
+  const Weights w = load_weights(m, b, B);
+  const int t0 = load_t0(m, b);
+  double x[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = x0[(size_t)i * B + b];
+  // costs[0]: zero gradient / Hessian (forward.py:130-134)
+  for (int i = 0; i < NX; ++i) {
+    p[(size_t)i * B + b] = 0.0;
+    for (int j = 0; j < NX; ++j) P[((size_t)i * NX + j) * B + b] = 0.0;
+  }
+  for (int t = 0; t < H; ++t) {
+    double u[NU], xn[NX], c, gsq, rec[L::stride];
+#pragma unroll
+    for (int k = 0; k < NU; ++k) u[k] = cmd[((size_t)t * NU + k) * B + b];
+    expand_step<M>(m, w, x, u, t0 + t + 1, xn, &c, &gsq, [&](int slot, double v) { rec[slot] = v; });
+    static_for<NX>([&](auto I) {
+      constexpr int i = I;
+      static_for<NX>([&](auto Jc) {
+        constexpr int j = Jc;
+        double a = (i == j) ? 1.0 : 0.0;
+        if constexpr (M::Nm(i, j)) a += rec[L::oN + M::Nm.slot(i, j)];
+        A[(((size_t)t * NX + i) * NX + j) * B + b] = a;
+        double pv = 0.0;
+        if constexpr (j >= i) { if constexpr (M::Pm(i, j)) pv = rec[L::oP + M::Pm.slot(i, j)]; }
+        else { if constexpr (M::Pm(j, i)) pv = rec[L::oP + M::Pm.slot(j, i)]; }
+        P[(((size_t)(t + 1) * NX + i) * NX + j) * B + b] = pv;
+      });
+      static_for<NU>([&](auto Kc) {
+        constexpr int k = Kc;
+        double bv = 0.0;
+        if constexpr (M::Bm(i, k)) bv = rec[L::oB + M::Bm.slot(i, k)];
+        Bm[(((size_t)t * NX + i) * NU + k) * B + b] = bv;
+      });
+      double pv = 0.0;
+      if constexpr (M::pm(0, i)) pv = rec[L::op + M::pm.slot(0, i)];
+      p[((size_t)(t + 1) * NX + i) * B + b] = pv;
+    });
+    for (int k = 0; k < NU; ++k) {
+      q[((size_t)t * NU + k) * B + b] = rec[L::oq + k];
+      for (int k2 = 0; k2 < NU; ++k2) Q[(((size_t)t * NU + k) * NU + k2) * B + b] = (k == k2) ? rec[L::oQ + k] : 0.0;
+    }
+    if (order >= 2) {
+      using S = Jet<M::NV, 2>;
+      S xs[NX], us[NU], xns[NX];
+      static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], M::sv(I)); });
+      static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], M::uv(I)); });
+      M::template step<S>(m, xs, us, xns);
+      double hl[sym_size(M::NV)];
+      for (int e = 0; e < sym_size(M::NV); ++e) {
+        double acc = 0.0;
+        for (int i = 0; i < NX; ++i) acc += lam[((size_t)t * NX + i) * B + b] * xns[i].h[e];
+        hl[e] = acc;
+      }
+      static_for<NX>([&](auto I) {
+        constexpr int i = I;
+        static_for<NX>([&](auto Jc) {
+          constexpr int j = Jc;
+          double v = 0.0;
+          if constexpr (M::sv(i) >= 0 && M::sv(j) >= 0) v = hl[sym_idx(M::sv(i), M::sv(j), M::NV)];
+          Hxx[(((size_t)t * NX + i) * NX + j) * B + b] = v;
+        });
+        static_for<NU>([&](auto Kc) {
+          constexpr int k = Kc;
+          double v = 0.0;
+          if constexpr (M::sv(i) >= 0 && M::uv(k) >= 0) v = hl[sym_idx(M::sv(i), M::uv(k), M::NV)];
+          Hxu[(((size_t)t * NX + i) * NU + k) * B + b] = v;
+        });
+      });
+      static_for<NU>([&](auto Kc) {
+        constexpr int k = Kc;
+        static_for<NU>([&](auto K2) {
+          constexpr int k2 = K2;
+          double v = 0.0;
+          if constexpr (M::uv(k) >= 0 && M::uv(k2) >= 0) v = hl[sym_idx(M::uv(k), M::uv(k2), M::NV)];
+          Huu[(((size_t)t * NU + k) * NU + k2) * B + b] = v;
+        });
+      });
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = xn[i];
+  }
+}
+}  // namespace
+
+template <>
+int Launch<ILQC_MODEL_INST>::forward(int order, const ilqc_model_desc& m, int B, const double* x0,
+                                     const double* cmd, double* lin, double* traj, double* cost_t, double* total,
+                                     double* cnorm, stream_t st) {
+  if (order == 0) ILQC_LAUNCH((forward_kernel<MI, 0>), B, kBlock, st, m, B, x0, cmd, lin, traj, cost_t, total, cnorm);
+  else ILQC_LAUNCH((forward_kernel<MI, 1>), B, kBlock, st, m, B, x0, cmd, lin, traj, cost_t, total, cnorm);
+  return ILQC_LAUNCH_OK();
+}
+
+template <>
+int Launch<ILQC_MODEL_INST>::expand_dense(const ilqc_model_desc& m, int B, const double* x0, const double* cmd,
+                                          int order, double* A, double* Bm, double* p, double* P, double* q,
+                                          double* Q, const double* lam, double* Hxx, double* Hxu, double* Huu,
+                                          stream_t st) {
+  ILQC_LAUNCH((expand_dense_kernel<MI>), B, kBlock, st, m, B, x0, cmd, order, A, Bm, p, P, q, Q, lam, Hxx, Hxu, Huu);
+  return ILQC_LAUNCH_OK();
+}
+
+template <>
+int Launch<ILQC_MODEL_INST>::backward(int mode, const ilqc_model_desc& m, int B, int n_slots, const int32_t* prob,
+                                      const int32_t* oslot, int n_oslots, const double* reg_ctrl, double reg_state,
+                                      const double* lin, const double* traj, const double* cmd, double* gains,
+                                      double* jcst, int32_t* feasible, stream_t st) {
+  if (mode == ILQC_BWD_LINQUAD)
+    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_LINQUAD>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots, reg_ctrl,
+                reg_state, lin, traj, cmd, gains, jcst, feasible);
+  else if (mode == ILQC_BWD_QUAD_NEWTON)
+    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_NEWTON>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots,
+                reg_ctrl, reg_state, lin, traj, cmd, gains, jcst, feasible);
+  else if (mode == ILQC_BWD_QUAD_DDP)
+    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_DDP>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots, reg_ctrl,
+                reg_state, lin, traj, cmd, gains, jcst, feasible);
+  else
+    return ILQC_E_ARG;
+  return ILQC_LAUNCH_OK();
+}
+
+template <>
+int Launch<ILQC_MODEL_INST>::rollout(int kind, const ilqc_model_desc& m, int B, int n_slots, const int32_t* prob,
+                                     const int32_t* gslot, int n_gslots, const int32_t* oslot, int n_oslots,
+                                     const double* step, const double* x0, const double* cmd, const double* traj,
+                                     const double* lin, const double* gains, const double* dir, double* diff,
+                                     double* newval, double* diffsq, stream_t st) {
+  if (kind == ILQC_ROLL_EXACT)
+    ILQC_LAUNCH((rollout_kernel<MI, ILQC_ROLL_EXACT>), n_slots, kBlock, st, m, B, n_slots, prob, gslot, n_gslots, oslot, n_oslots,
+                step, x0, cmd, traj, lin, gains, dir, diff, newval, diffsq);
+  else if (kind == ILQC_ROLL_LIN)
+    ILQC_LAUNCH((rollout_kernel<MI, ILQC_ROLL_LIN>), n_slots, kBlock, st, m, B, n_slots, prob, gslot, n_gslots, oslot, n_oslots,
+                step, x0, cmd, traj, lin, gains, dir, diff, newval, diffsq);
+  else if (kind == ILQC_ROLL_GD)
+    ILQC_LAUNCH((rollout_kernel<MI, ILQC_ROLL_GD>), n_slots, kBlock, st, m, B, n_slots, prob, gslot, n_gslots, oslot, n_oslots, step,
+                x0, cmd, traj, lin, gains, dir, diff, newval, diffsq);
+  else
+    return ILQC_E_ARG;
+  return ILQC_LAUNCH_OK();
+}
+
+template <>
+int Launch<ILQC_MODEL_INST>::adjoint(const ilqc_model_desc& m, int B, const double* lin, double* grad,
+                                     double* gnorm, stream_t st) {
+  ILQC_LAUNCH((adjoint_kernel<MI>), B, kBlock, st, m, B, lin, grad, gnorm);
+  return ILQC_LAUNCH_OK();
+}
+
+template <>
+void Launch<ILQC_MODEL_INST>::dims(int* nx, int* nu, int* lin_stride, int* gain_stride) {
+  *nx = MI::NX;
+  *nu = MI::NU;
+  *lin_stride = Layout<MI>::stride;
+  *gain_stride = Layout<MI>::gain_stride;
+}
+
+}  // namespace ilqc

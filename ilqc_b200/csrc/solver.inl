@@ -1,0 +1,443 @@
+// Batched run_min_algo: the outer loop, the per-problem line-search state machine and the metrics /
+// convergence bookkeeping of the reference, for B independent problems at once.
+//
+// Reference semantics restated (file:line in /root/reference):
+//   run_min_algo, collect_info, check_cvg_status     algorithms/run_min_algo.py:15-100, :127-264
+//   min_step (line-search set-up per step mode)      algorithms/algos_steps.py:277-381
+//   backtracking_line_search                         algorithms/algos_steps.py:384-437
+//   gd_oracle / classic_oracle / ddp_oracle          algorithms/algos_steps.py:22-43, :105-274
+//
+// B200-first structure: every problem is a row of a structure-of-arrays workspace resident in HBM; one
+// solver iteration is a handful of launches (expansion, L line-search candidates per still-searching
+// problem = backward + roll-out, selection, adjoint, status) with thread-per-(problem,candidate)
+// kernels.  Problems whose line search needs more trips are compacted into a dense index list so later
+// rounds launch only the threads that still have work.  The only host<->device traffic inside the loop
+// is one 4-byte counter per line-search round.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include "launch.cuh"
+
+namespace ilqc {
+
+// ---- memory plumbing (stream-ordered) -----------------------------------------------------------------
+#if defined(ILQC_HOSTSIM)
+inline int dev_memset(void* p, int v, size_t n, stream_t) { memset(p, v, n); return 0; }
+inline int dev_d2h_sync(void* dst, const void* src, size_t n, stream_t) { memcpy(dst, src, n); return 0; }
+inline int dev_h2d(void* dst, const void* src, size_t n, stream_t) { memcpy(dst, src, n); return 0; }
+inline int dev_d2h(void* dst, const void* src, size_t n, stream_t) { memcpy(dst, src, n); return 0; }
+inline int dev_d2d(void* dst, const void* src, size_t n, stream_t) { memcpy(dst, src, n); return 0; }
+inline int dev_sync(stream_t) { return 0; }
+#else
+inline int dev_memset(void* p, int v, size_t n, stream_t st) { return (int)cudaMemsetAsync(p, v, n, st); }
+inline int dev_d2h_sync(void* dst, const void* src, size_t n, stream_t st) {
+  cudaError_t e = cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaStreamSynchronize(st);
+}
+inline int dev_h2d(void* dst, const void* src, size_t n, stream_t st) {
+  return (int)cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st);
+}
+inline int dev_d2h(void* dst, const void* src, size_t n, stream_t st) {
+  return (int)cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st);
+}
+inline int dev_d2d(void* dst, const void* src, size_t n, stream_t st) {
+  return (int)cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, st);
+}
+inline int dev_sync(stream_t st) { return (int)cudaStreamSynchronize(st); }
+#endif
+
+// ---- model dispatch -----------------------------------------------------------------------------------
+#define ILQC_FOR_MODEL(model_id, CALL)                                   \
+  switch (model_id) {                                                    \
+    case ILQC_MODEL_PENDULUM: { using LM = Launch<ILQC_MODEL_PENDULUM>; CALL; } break;       \
+    case ILQC_MODEL_CARTPOLE: { using LM = Launch<ILQC_MODEL_CARTPOLE>; CALL; } break;       \
+    case ILQC_MODEL_CAR_SIMPLE: { using LM = Launch<ILQC_MODEL_CAR_SIMPLE>; CALL; } break;   \
+    case ILQC_MODEL_CAR_BICYCLE: { using LM = Launch<ILQC_MODEL_CAR_BICYCLE>; CALL; } break; \
+    default: return ILQC_E_ARG;                                          \
+  }
+
+struct Dims { int nx, nu, lin_stride, gain_stride; };
+inline int get_dims(const ilqc_model_desc* m, Dims* d) {
+  if (!m) return ILQC_E_ARG;
+  if (m->integrator == ILQC_INT_RK4) return ILQC_E_UNSUPPORTED;  // 3-controls-per-step RK4: SURVEY 8(f)-1, not built yet
+  if (m->model >= ILQC_MODEL_CAR_SIMPLE && m->cost == ILQC_COST_CONTOURING && m->time_penalty == ILQC_TP_DREF_SQUARED)
+    return ILQC_E_UNSUPPORTED;  // adds a (tref,vtref) cross term outside the stored pattern
+  if (m->model >= ILQC_MODEL_CAR_SIMPLE && m->termination != ILQC_TERM_LOOP) return ILQC_E_UNSUPPORTED;
+  ILQC_FOR_MODEL(m->model, LM::dims(&d->nx, &d->nu, &d->lin_stride, &d->gain_stride));
+  return 0;
+}
+
+// ---- bookkeeping kernels ------------------------------------------------------------------------------
+namespace {
+
+struct LsParams {
+  int algo_type, approx, step_mode, L, line_search, H, nu;
+  double rho;
+};
+
+// min_step's line-search set-up (algos_steps.py:333-367): first trial step of every running problem
+ILQC_GLOBAL ls_init_kernel(LsParams P, int B, const int32_t* status, const double* stepsize, const double* cnorm,
+                           double* s_try, int32_t* flags, int32_t* trips) {
+  const int b = ILQC_TID;
+  if (b >= B) return;
+  int act = status[b] == ILQC_RUNNING;
+  if (act) {
+    double s = stepsize[b];
+    if (P.line_search) {
+      if (P.step_mode == ILQC_STEP_DIR) s = 1.0;
+      else if (P.step_mode == ILQC_STEP_REG) s = (8.0 * s) / cnorm[b];
+      else if (P.step_mode == ILQC_STEP_REGVAR) s = s * 8.0;
+      else s = ::fmin(4.0 * s, 1.0);
+    }
+    s_try[b] = s;
+    trips[b] = 0;
+  }
+  flags[b] = act;
+}
+
+// ordered compaction of the flagged problems into list[0..count)
+#if defined(ILQC_HOSTSIM)
+ILQC_GLOBAL compact_kernel(int B, const int32_t* flags, int32_t* list, int32_t* count) {
+  int n = 0;
+  for (int b = 0; b < B; ++b)
+    if (flags[b]) list[n++] = b;
+  *count = n;
+}
+#else
+__global__ void compact_kernel(int B, const int32_t* flags, int32_t* list, int32_t* count) {
+  __shared__ int sums[1024];
+  const int tid = threadIdx.x;
+  const int chunk = (B + 1023) / 1024;
+  const int lo = tid * chunk, hi = min(B, lo + chunk);
+  int n = 0;
+  for (int b = lo; b < hi; ++b) n += flags[b] != 0;
+  sums[tid] = n;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int v = (tid >= off) ? sums[tid - off] : 0;
+    __syncthreads();
+    sums[tid] += v;
+    __syncthreads();
+  }
+  int pos = sums[tid] - n;
+  for (int b = lo; b < hi; ++b)
+    if (flags[b]) list[pos++] = b;
+  if (tid == 1023) *count = sums[1023];
+}
+#endif
+
+// candidates c < L of every still-searching problem: s_c = s_try * rho^c by repeated multiplication
+// (algos_steps.py:420 `stepsize *= decrease_fac`), reg_ctrl = 1/s_c for the regularised oracles (:164, :244)
+ILQC_GLOBAL make_slots_kernel(LsParams P, int n_active, const int32_t* list, const double* s_try, int32_t* prob,
+                              int32_t* gslot, double* step_true, double* step_roll, double* reg) {
+  const int a = ILQC_TID;
+  if (a >= n_active) return;
+  const int b = list[a];
+  double s = s_try[b];
+  const bool regmode = (P.step_mode == ILQC_STEP_REG || P.step_mode == ILQC_STEP_REGVAR);
+  for (int c = 0; c < P.L; ++c) {
+    const int slot = a * P.L + c;
+    prob[slot] = b;
+    step_true[slot] = s;
+    if (P.algo_type == ILQC_ALGO_GD) {
+      step_roll[slot] = -s;  // diff = -stepsize * grad (algos_steps.py:40)
+      gslot[slot] = b;
+    } else if (regmode) {
+      step_roll[slot] = 1.0;  // roll_out_*(…, stepsize=1.0) with gains of reg = 1/s
+      reg[slot] = 1.0 / s;
+      gslot[slot] = slot;
+    } else {
+      step_roll[slot] = s;  // gains of the single backward pass, scaled offsets
+      gslot[slot] = b;
+    }
+    s *= P.rho;
+  }
+}
+
+// backtracking_line_search's accept / stop tests (algos_steps.py:411-434) for the L candidates of every
+// still-searching problem, in the order the sequential reference would try them.
+ILQC_GLOBAL ls_select_kernel(LsParams P, int n_active, int B, int n_slots, const int32_t* list,
+                             const double* step_true, const double* newval, const double* diffsq,
+                             const double* jcst_slot, const double* dec_unit, const int32_t* feas_slot,
+                             const int32_t* feas_prob, const double* diff, const double* cnorm, double* cmd,
+                             double* curr_val, double* stepsize, double* s_try, int32_t* status, int32_t* flags,
+                             int32_t* trips, int max_trips) {
+  const int a = ILQC_TID;
+  if (a >= n_active) return;
+  const int b = list[a];
+  const bool regmode = (P.step_mode == ILQC_STEP_REG || P.step_mode == ILQC_STEP_REGVAR);
+  const double curr = curr_val[b];
+  int chosen = -1;
+  bool chosen_feasible = false;
+  int ntrip = trips[b];
+  for (int c = 0; c < P.L && chosen < 0; ++c) {
+    const int slot = a * P.L + c;
+    const double s = step_true[slot];
+    bool feasible = true;
+    if (P.algo_type != ILQC_ALGO_GD) feasible = regmode ? (feas_slot[slot] != 0) : (feas_prob[b] != 0);
+    ++ntrip;
+    bool decrease = false, stop = false;
+    if (feasible) {
+      // dec_obj: regularised oracles return the model decrease jcst of their own backward pass; direction
+      // oracles scale the unit-step value (stepsize*opt_step, :157 / :237 ; gd: stepsize*fixed_obj, :41)
+      const double dec = regmode && P.algo_type != ILQC_ALGO_GD ? jcst_slot[slot] : s * dec_unit[b];
+      const double dirn = s > 0.0 ? 1.0 : (s < 0.0 ? -1.0 : 0.0);
+      decrease = dirn * (newval[slot] - (curr + dec)) < 0.0;
+      stop = ::sqrt(diffsq[slot]) < 1e-32;
+    } else {
+      stop = ::fabs(s) < 1e-32;
+    }
+    if (!P.line_search) { decrease = true; }
+    if (decrease || stop || ntrip >= max_trips) {
+      chosen = c;
+      chosen_feasible = feasible;
+    }
+  }
+  trips[b] = ntrip;
+  if (chosen >= 0) {
+    const int slot = a * P.L + chosen;
+    if (chosen_feasible) {
+      const int n = P.H * P.nu;
+      for (int e = 0; e < n; ++e) cmd[(size_t)e * B + b] += diff[(size_t)e * n_slots + slot];
+      curr_val[b] = newval[slot];
+      if (P.line_search) {
+        const double s = step_true[slot];
+        stepsize[b] = (P.step_mode == ILQC_STEP_REG && P.algo_type != ILQC_ALGO_GD) ? s * cnorm[b] : s;
+      }
+    } else {
+      status[b] = ILQC_NO_DIRECTION;  // min_step returns None (algos_steps.py:379-380)
+      curr_val[b] = NAN;
+    }
+    flags[b] = 0;
+  } else {
+    s_try[b] = step_true[a * P.L + P.L - 1] * P.rho;
+    flags[b] = 1;
+  }
+}
+
+// collect_info + check_cvg_status (run_min_algo.py:127-264) for metrics row `it`
+ILQC_GLOBAL status_kernel(LsParams P, int B, int it, const double* curr_val, const double* gnorm,
+                          const double* stepsize, double* cost, double* gn, double* step_rep, int32_t* status,
+                          int32_t* n_done) {
+  const int b = ILQC_TID;
+  if (b >= B) return;
+  const size_t row = (size_t)it * B + b;
+  const int st_prev = status[b];
+  if (it > 0 && st_prev != ILQC_RUNNING) {
+    // stopped in an earlier iteration: pad.  A problem whose line search found no direction in THIS
+    // iteration records a NaN cost once (collect_info with costs=None, run_min_algo.py:154).
+    const bool failed_now = st_prev == ILQC_NO_DIRECTION && n_done[b] == it - 1;
+    cost[row] = NAN; gn[row] = NAN; step_rep[row] = failed_now ? stepsize[b] : NAN;
+    if (failed_now) n_done[b] = it;
+    return;
+  }
+  const double c = curr_val[b];
+  double srep = stepsize[b];
+  // the reported step of the 'reg' mode is rescaled by the previous gradient norm (run_min_algo.py:158-161)
+  if (P.algo_type != ILQC_ALGO_GD && P.step_mode == ILQC_STEP_REG && it > 0) srep = srep * gn[(size_t)(it - 1) * B + b];
+  cost[row] = c;
+  gn[row] = gnorm[b];
+  step_rep[row] = srep;
+  n_done[b] = it;
+  int st = ILQC_RUNNING;
+  const double c0 = cost[b];
+  if (c != c || c > c0 + 1e3) st = ILQC_DIVERGED;
+  if (it > 0) {
+    const double cp = cost[(size_t)(it - 1) * B + b];
+    if (::fabs(c - cp) / ::fabs(cp) < 1e-24) st = ILQC_CONVERGED;
+  }
+  if (st == ILQC_RUNNING && srep < 1e-24) st = ILQC_STUCK;
+  status[b] = st;
+}
+
+ILQC_GLOBAL fill_kernel(int n, double* p, double v) {
+  const int i = ILQC_TID;
+  if (i < n) p[i] = v;
+}
+ILQC_GLOBAL fill_i32_kernel(int n, int32_t* p, int32_t v) {
+  const int i = ILQC_TID;
+  if (i < n) p[i] = v;
+}
+// gd: dec_unit = -||grad||^2/2 (algos_steps.py:38) ; direction oracles: dec_unit = jcst of the backward pass
+ILQC_GLOBAL gd_dec_kernel(int B, const double* gnorm, double* dec_unit) {
+  const int b = ILQC_TID;
+  if (b < B) dec_unit[b] = -0.5 * (gnorm[b] * gnorm[b]);
+}
+// direction oracles escalate reg_ctrl 1e-6, 1e-5, ... while the backward pass is infeasible and reg<1e6
+// (algos_steps.py:140-144, :220-224): flag the problems that still need another pass
+ILQC_GLOBAL escalate_kernel(int B, const int32_t* status, const int32_t* feas, double* reg, int32_t* flags) {
+  const int b = ILQC_TID;
+  if (b >= B) return;
+  int f = 0;
+  if (status[b] == ILQC_RUNNING && !feas[b] && reg[b] < 1e6) {
+    reg[b] = reg[b] > 0.0 ? 10.0 * reg[b] : 1e-6;
+    f = 1;
+  }
+  flags[b] = f;
+}
+// [B][n] -> [n][B] and back (reference layout <-> engine layout)
+ILQC_GLOBAL to_soa_kernel(const double* src, double* dst, int B, int n) {
+  const int i = ILQC_TID;
+  if (i >= B * n) return;
+  const int b = i % B, e = i / B;
+  dst[i] = src[(size_t)b * n + e];
+}
+ILQC_GLOBAL from_soa_kernel(const double* src, double* dst, int B, int n) {
+  const int i = ILQC_TID;
+  if (i >= B * n) return;
+  const int e = i % n, b = i / n;
+  dst[i] = src[(size_t)e * B + b];
+}
+
+}  // namespace
+
+// ---- workspace ----------------------------------------------------------------------------------------
+struct Workspace {
+  double *lin, *traj, *gains, *diff, *dir, *newval, *diffsq, *jcst, *step_true, *step_roll, *reg, *curr_val,
+      *cnorm, *gnorm, *s_try, *dec_unit, *reg_prob;
+  int32_t *prob, *gslot, *feas_slot, *feas_prob, *list, *flags, *trips, *count, *ident;
+  size_t bytes;
+};
+inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+inline void carve(Workspace* w, char* base, const Dims& d, int H, int B, int L) {
+  size_t off = 0;
+  auto takeD = [&](size_t n) { double* p = (double*)(base + off); off = align_up(off + n * sizeof(double)); return p; };
+  auto takeI = [&](size_t n) { int32_t* p = (int32_t*)(base + off); off = align_up(off + n * sizeof(int32_t)); return p; };
+  const size_t S = (size_t)B * L;
+  w->lin = takeD((size_t)H * d.lin_stride * B);
+  w->traj = takeD((size_t)(H + 1) * d.nx * B);
+  w->gains = takeD((size_t)H * d.gain_stride * S);
+  w->diff = takeD((size_t)H * d.nu * S);
+  w->dir = takeD((size_t)H * d.nu * B);
+  w->newval = takeD(S); w->diffsq = takeD(S); w->jcst = takeD(S); w->step_true = takeD(S); w->step_roll = takeD(S);
+  w->reg = takeD(S);
+  w->curr_val = takeD(B); w->cnorm = takeD(B); w->gnorm = takeD(B); w->s_try = takeD(B); w->dec_unit = takeD(B);
+  w->reg_prob = takeD(B);
+  w->prob = takeI(S); w->gslot = takeI(S); w->feas_slot = takeI(S);
+  w->feas_prob = takeI(B); w->list = takeI(B); w->flags = takeI(B); w->trips = takeI(B); w->ident = takeI(B);
+  w->count = takeI(64);
+  w->bytes = off;
+}
+
+inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const double* x0, double* cmd,
+                      double* stepsize, int n_iter, double* cost, double* gnorm_out, double* step_rep,
+                      int32_t* n_done, int32_t* status, int32_t* ls_trips, void* workspace, size_t workspace_bytes,
+                      stream_t st) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (!a || B <= 0 || n_iter < 0 || a->n_candidates < 1) return ILQC_E_ARG;
+  const int H = m->horizon, L = a->n_candidates;
+  Workspace w;
+  carve(&w, (char*)workspace, d, H, B, L);
+  if (!workspace || workspace_bytes < w.bytes) return ILQC_E_WORKSPACE;
+
+  LsParams P;
+  P.algo_type = a->algo_type; P.approx = a->approx; P.step_mode = a->step_mode; P.L = L;
+  P.line_search = a->line_search; P.H = H; P.nu = d.nu;
+  if (a->algo_type == ILQC_ALGO_GD) P.step_mode = ILQC_STEP_REGVAR;  // min_step forces it (algos_steps.py:311)
+  const bool regmode = (P.step_mode == ILQC_STEP_REG || P.step_mode == ILQC_STEP_REGVAR);
+  P.rho = regmode ? 0.5 : 0.9;
+  const int max_trips = a->max_ls_trips > 0 ? a->max_ls_trips : 2000;
+  const bool quad = a->approx == ILQC_APPROX_QUAD && a->algo_type != ILQC_ALGO_GD;
+  const int bwd_mode = !quad ? ILQC_BWD_LINQUAD
+                             : (a->algo_type == ILQC_ALGO_DDP ? ILQC_BWD_QUAD_DDP : ILQC_BWD_QUAD_NEWTON);
+  const bool need_grad = a->compute_grad_norm || a->algo_type == ILQC_ALGO_GD;
+  const ilqc_model_desc& md = *m;
+
+#define ILQC_CHECK(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+  ILQC_LAUNCH((fill_i32_kernel), B, 256, st, B, status, (int32_t)ILQC_RUNNING);
+  ILQC_LAUNCH((fill_i32_kernel), B, 256, st, B, n_done, (int32_t)0);
+  ILQC_LAUNCH((fill_i32_kernel), B, 256, st, B, w.feas_prob, (int32_t)1);
+  ILQC_LAUNCH((fill_kernel), B, 256, st, B, w.gnorm, (double)NAN);
+
+  // iteration 0: objective of the initial controls (same arithmetic as every candidate evaluation), its
+  // expansion and the metrics row 0 (run_min_algo.py:65-76)
+  ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(0, md, B, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st)));
+  ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st)));
+  if (need_grad) ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, w.lin, w.dir, w.gnorm, st)));
+  ILQC_LAUNCH((status_kernel), B, 256, st, P, B, 0, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
+              n_done);
+
+  for (int it = 1; it <= n_iter; ++it) {
+    ILQC_LAUNCH((ls_init_kernel), B, 256, st, P, B, status, stepsize, w.cnorm, w.s_try, w.flags, w.trips);
+    ILQC_LAUNCH((compact_kernel), 1, 1024, st, B, w.flags, w.list, w.count);
+    int n_active = 0;
+    ILQC_CHECK(dev_d2h_sync(&n_active, w.count, sizeof(int), st));
+    if (n_active == 0) {
+      for (int r = it; r <= n_iter; ++r)
+        ILQC_LAUNCH((status_kernel), B, 256, st, P, B, r, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep,
+                    status, n_done);
+      break;
+    }
+    if (a->algo_type == ILQC_ALGO_GD) {
+      ILQC_LAUNCH((gd_dec_kernel), B, 256, st, B, w.gnorm, w.dec_unit);
+    } else if (!regmode) {
+      // direction oracles: one backward pass per problem (reg_ctrl = 0, escalated while infeasible)
+      ILQC_LAUNCH((fill_kernel), B, 256, st, B, w.reg_prob, 0.0);
+      const int32_t* plist = w.list;
+      int n_pass = n_active;
+      for (int esc = 0; esc < 16 && n_pass > 0; ++esc) {
+        // slot == problem for these gains: thread a serves problem plist[a] and writes slot plist[a]
+        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::backward(bwd_mode, md, B, n_pass, plist, plist, B, w.reg_prob, 0.0, w.lin,
+                                                         w.traj, cmd, w.gains, w.dec_unit, w.feas_prob, st)));
+        if (!quad) break;
+        ILQC_LAUNCH((escalate_kernel), B, 256, st, B, status, w.feas_prob, w.reg_prob, w.flags);
+        ILQC_LAUNCH((compact_kernel), 1, 1024, st, B, w.flags, w.ident, w.count);
+        ILQC_CHECK(dev_d2h_sync(&n_pass, w.count, sizeof(int), st));
+        plist = w.ident;
+      }
+      if (a->algo_type == ILQC_ALGO_CLASSIC) {
+        // diff_cmd = roll_out_lin(traj, gains) once (algos_steps.py:153), candidates scale it
+        ILQC_LAUNCH((fill_kernel), B, 256, st, B, w.step_roll, 1.0);
+        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(ILQC_ROLL_LIN, md, B, n_active, w.list, w.list, B, w.list, B,
+                                                        w.step_roll, x0, cmd, w.traj, w.lin, w.gains, nullptr, w.dir,
+                                                        w.newval, w.diffsq, st)));
+      }
+      // restore the active flags consumed by the escalation loop
+      ILQC_LAUNCH((ls_init_kernel), B, 256, st, P, B, status, stepsize, w.cnorm, w.s_try, w.flags, w.trips);
+    }
+
+    // ---- line search rounds ----
+    while (n_active > 0) {
+      const int n_slots = n_active * L;
+      ILQC_LAUNCH((make_slots_kernel), n_active, 256, st, P, n_active, w.list, w.s_try, w.prob, w.gslot, w.step_true,
+                  w.step_roll, w.reg);
+      if (a->algo_type == ILQC_ALGO_GD) {
+        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(ILQC_ROLL_GD, md, B, n_slots, w.prob, nullptr, 0, nullptr, n_slots, w.step_roll, x0,
+                                                        cmd, w.traj, w.lin, nullptr, w.dir, w.diff, w.newval, w.diffsq,
+                                                        st)));
+      } else if (regmode) {
+        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::backward(bwd_mode, md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
+                                                         w.gains, w.jcst, w.feas_slot, st)));
+        const int kind = a->algo_type == ILQC_ALGO_DDP ? ILQC_ROLL_EXACT : ILQC_ROLL_LIN;
+        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, nullptr, n_slots, nullptr, n_slots, w.step_roll, x0, cmd,
+                                                        w.traj, w.lin, w.gains, nullptr, w.diff, w.newval, w.diffsq,
+                                                        st)));
+      } else {
+        const int kind = a->algo_type == ILQC_ALGO_DDP ? ILQC_ROLL_EXACT : ILQC_ROLL_GD;
+        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, w.gslot, B, nullptr, n_slots, w.step_roll, x0, cmd,
+                                                        w.traj, w.lin, w.gains, w.dir, w.diff, w.newval, w.diffsq, st)));
+      }
+      ILQC_LAUNCH((ls_select_kernel), n_active, 128, st, P, n_active, B, n_slots, w.list, w.step_true, w.newval, w.diffsq,
+                  w.jcst, w.dec_unit, w.feas_slot, w.feas_prob, w.diff, w.cnorm, cmd, w.curr_val, stepsize, w.s_try,
+                  status, w.flags, w.trips, max_trips);
+      ILQC_LAUNCH((compact_kernel), 1, 1024, st, B, w.flags, w.list, w.count);
+      ILQC_CHECK(dev_d2h_sync(&n_active, w.count, sizeof(int), st));
+    }
+    if (ls_trips) ILQC_CHECK(dev_d2d(ls_trips + (size_t)(it - 1) * B, w.trips, sizeof(int32_t) * B, st));
+
+    // re-expand at the accepted controls (algos_steps.py:376-378) and collect the metrics of this iteration
+    ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st)));
+    if (need_grad) ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, w.lin, w.dir, w.gnorm, st)));
+    ILQC_LAUNCH((status_kernel), B, 256, st, P, B, it, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
+                n_done);
+  }
+  ILQC_CHECK(dev_sync(st));
+  return ILQC_LAUNCH_OK();
+#undef ILQC_CHECK
+}
+
+}  // namespace ilqc
