@@ -74,6 +74,8 @@ PROTOTYPES = {
     "ilqc_solve_host": (C.c_int, [_MP, _AP, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "ilqc_to_soa": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
     "ilqc_from_soa": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
+    "ilqc_profile_enable": (C.c_int, [C.c_int]),
+    "ilqc_profile_read": (C.c_int, [C.POINTER(_d), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
     "ilqc_fp64_peak": (C.c_int, [C.c_int, C.POINTER(_d), _p]),
 }
 

@@ -140,6 +140,19 @@ int ilqc_solve(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const d
                     workspace_bytes, (stream_t)stream);
 }
 
+// per-kernel-class CUDA-event timing of ilqc_solve (classes: 0 roll-out+cost, 1 expansion, 2 backward,
+// 3 candidate roll-out, 4 adjoint).  enable: 1/0 ; read returns cumulative ms / launches / slots and resets.
+int ilqc_profile_enable(int enable) { prof_state().enabled = enable; return 0; }
+int ilqc_profile_read(double* ms, int64_t* launches, int64_t* units, int n) {
+  if (!ms || !launches || !units || n < PROF_N) return ILQC_E_ARG;
+  ProfState& p = prof_state();
+  for (int i = 0; i < PROF_N; ++i) {
+    ms[i] = p.ms[i]; launches[i] = p.launches[i]; units[i] = p.units[i];
+    p.ms[i] = 0; p.launches[i] = 0; p.units[i] = 0;
+  }
+  return PROF_N;
+}
+
 int ilqc_to_soa(const double* src, double* dst, int B, int n, void* stream) {
   if (!src || !dst || B <= 0 || n <= 0) return ILQC_E_ARG;
   ILQC_LAUNCH((to_soa_kernel), B * n, 256, (stream_t)stream, src, dst, B, n);

@@ -16,6 +16,7 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <vector>
 #include "launch.cuh"
 
 namespace ilqc {
@@ -56,6 +57,45 @@ inline int dev_sync(stream_t st) { return (int)cudaStreamSynchronize(st); }
     case ILQC_MODEL_CAR_BICYCLE: { using LM = Launch<ILQC_MODEL_CAR_BICYCLE>; CALL; } break; \
     default: return ILQC_E_ARG;                                          \
   }
+
+// ---- optional per-kernel-class timing with CUDA events (ilqc_profile_*; used by bench.py for the roofline) ----
+enum { PROF_FORWARD0 = 0, PROF_LINEARIZE = 1, PROF_BACKWARD = 2, PROF_ROLLOUT = 3, PROF_ADJOINT = 4, PROF_N = 5 };
+struct ProfState {
+  int enabled = 0;
+  double ms[PROF_N] = {0, 0, 0, 0, 0};
+  long long launches[PROF_N] = {0, 0, 0, 0, 0};
+  long long units[PROF_N] = {0, 0, 0, 0, 0};  // slots (threads with work) summed over launches
+};
+inline ProfState& prof_state() { static ProfState s; return s; }
+#if defined(ILQC_HOSTSIM)
+struct ProfScope { ProfScope(stream_t) {} void begin(int, long long) {} void end() {} void flush() {} };
+#else
+struct ProfScope {
+  struct Rec { int cls; long long units; cudaEvent_t e0, e1; };
+  std::vector<Rec> recs;
+  stream_t st;
+  bool on;
+  explicit ProfScope(stream_t s) : st(s), on(prof_state().enabled != 0) {}
+  void begin(int cls, long long units) {
+    if (!on) return;
+    Rec r; r.cls = cls; r.units = units;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    recs.push_back(r);
+  }
+  void end() { if (on) cudaEventRecord(recs.back().e1, st); }
+  void flush() {  // call after the stream has been synchronised
+    for (auto& r : recs) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.e0, r.e1);
+      prof_state().ms[r.cls] += ms; prof_state().launches[r.cls] += 1; prof_state().units[r.cls] += r.units;
+      cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    recs.clear();
+  }
+};
+#endif
+#define ILQC_PROF(cls, units, stmt) do { prof.begin(cls, units); stmt; prof.end(); } while (0)
 
 struct Dims { int nx, nu, lin_stride, gain_stride; };
 inline int get_dims(const ilqc_model_desc* m, Dims* d) {
@@ -333,6 +373,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
   carve(&w, (char*)workspace, d, H, B, L);
   if (!workspace || workspace_bytes < w.bytes) return ILQC_E_WORKSPACE;
 
+  ProfScope prof(st);
   LsParams P;
   P.algo_type = a->algo_type; P.approx = a->approx; P.step_mode = a->step_mode; P.L = L;
   P.line_search = a->line_search; P.H = H; P.nu = d.nu;
@@ -355,9 +396,9 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
 
   // iteration 0: objective of the initial controls (same arithmetic as every candidate evaluation), its
   // expansion and the metrics row 0 (run_min_algo.py:65-76)
-  ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(0, md, B, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st)));
-  ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st)));
-  if (need_grad) ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, w.lin, w.dir, w.gnorm, st)));
+  ILQC_PROF(PROF_FORWARD0, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(0, md, B, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st))));
+  ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
+  if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, w.lin, w.dir, w.gnorm, st))));
   ILQC_LAUNCH((status_kernel), B, 256, st, P, B, 0, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
               n_done);
 
@@ -381,8 +422,8 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
       int n_pass = n_active;
       for (int esc = 0; esc < 16 && n_pass > 0; ++esc) {
         // slot == problem for these gains: thread a serves problem plist[a] and writes slot plist[a]
-        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::backward(bwd_mode, md, B, n_pass, plist, plist, B, w.reg_prob, 0.0, w.lin,
-                                                         w.traj, cmd, w.gains, w.dec_unit, w.feas_prob, st)));
+        ILQC_PROF(PROF_BACKWARD, n_pass, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::backward(bwd_mode, md, B, n_pass, plist, plist, B, w.reg_prob, 0.0, w.lin,
+                                                         w.traj, cmd, w.gains, w.dec_unit, w.feas_prob, st))));
         if (!quad) break;
         ILQC_LAUNCH((escalate_kernel), B, 256, st, B, status, w.feas_prob, w.reg_prob, w.flags);
         ILQC_LAUNCH((compact_kernel), 1, 1024, st, B, w.flags, w.ident, w.count);
@@ -392,9 +433,9 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
       if (a->algo_type == ILQC_ALGO_CLASSIC) {
         // diff_cmd = roll_out_lin(traj, gains) once (algos_steps.py:153), candidates scale it
         ILQC_LAUNCH((fill_kernel), B, 256, st, B, w.step_roll, 1.0);
-        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(ILQC_ROLL_LIN, md, B, n_active, w.list, w.list, B, w.list, B,
+        ILQC_PROF(PROF_ROLLOUT, n_active, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(ILQC_ROLL_LIN, md, B, n_active, w.list, w.list, B, w.list, B,
                                                         w.step_roll, x0, cmd, w.traj, w.lin, w.gains, nullptr, w.dir,
-                                                        w.newval, w.diffsq, st)));
+                                                        w.newval, w.diffsq, st))));
       }
       // restore the active flags consumed by the escalation loop
       ILQC_LAUNCH((ls_init_kernel), B, 256, st, P, B, status, stepsize, w.cnorm, w.s_try, w.flags, w.trips);
@@ -406,20 +447,20 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
       ILQC_LAUNCH((make_slots_kernel), n_active, 256, st, P, n_active, w.list, w.s_try, w.prob, w.gslot, w.step_true,
                   w.step_roll, w.reg);
       if (a->algo_type == ILQC_ALGO_GD) {
-        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(ILQC_ROLL_GD, md, B, n_slots, w.prob, nullptr, 0, nullptr, n_slots, w.step_roll, x0,
+        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(ILQC_ROLL_GD, md, B, n_slots, w.prob, nullptr, 0, nullptr, n_slots, w.step_roll, x0,
                                                         cmd, w.traj, w.lin, nullptr, w.dir, w.diff, w.newval, w.diffsq,
-                                                        st)));
+                                                        st))));
       } else if (regmode) {
-        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::backward(bwd_mode, md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
-                                                         w.gains, w.jcst, w.feas_slot, st)));
+        ILQC_PROF(PROF_BACKWARD, n_slots, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::backward(bwd_mode, md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
+                                                         w.gains, w.jcst, w.feas_slot, st))));
         const int kind = a->algo_type == ILQC_ALGO_DDP ? ILQC_ROLL_EXACT : ILQC_ROLL_LIN;
-        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, nullptr, n_slots, nullptr, n_slots, w.step_roll, x0, cmd,
+        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, nullptr, n_slots, nullptr, n_slots, w.step_roll, x0, cmd,
                                                         w.traj, w.lin, w.gains, nullptr, w.diff, w.newval, w.diffsq,
-                                                        st)));
+                                                        st))));
       } else {
         const int kind = a->algo_type == ILQC_ALGO_DDP ? ILQC_ROLL_EXACT : ILQC_ROLL_GD;
-        ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, w.gslot, B, nullptr, n_slots, w.step_roll, x0, cmd,
-                                                        w.traj, w.lin, w.gains, w.dir, w.diff, w.newval, w.diffsq, st)));
+        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, w.gslot, B, nullptr, n_slots, w.step_roll, x0, cmd,
+                                                        w.traj, w.lin, w.gains, w.dir, w.diff, w.newval, w.diffsq, st))));
       }
       ILQC_LAUNCH((ls_select_kernel), n_active, 128, st, P, n_active, B, n_slots, w.list, w.step_true, w.newval, w.diffsq,
                   w.jcst, w.dec_unit, w.feas_slot, w.feas_prob, w.diff, w.cnorm, cmd, w.curr_val, stepsize, w.s_try,
@@ -430,12 +471,13 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
     if (ls_trips) ILQC_CHECK(dev_d2d(ls_trips + (size_t)(it - 1) * B, w.trips, sizeof(int32_t) * B, st));
 
     // re-expand at the accepted controls (algos_steps.py:376-378) and collect the metrics of this iteration
-    ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st)));
-    if (need_grad) ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, w.lin, w.dir, w.gnorm, st)));
+    ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
+    if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, w.lin, w.dir, w.gnorm, st))));
     ILQC_LAUNCH((status_kernel), B, 256, st, P, B, it, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
                 n_done);
   }
   ILQC_CHECK(dev_sync(st));
+  prof.flush();
   return ILQC_LAUNCH_OK();
 #undef ILQC_CHECK
 }

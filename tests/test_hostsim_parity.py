@@ -1,0 +1,32 @@
+"""CPU (`-m "not gpu"`) checks of the kernel arithmetic: the templates of ilqc_b200/csrc compiled for the
+host (tests/hostsim) against golden vectors of the unmodified reference.  The GPU tests
+(test_gpu_parity.py) run the same checks through the CUDA library."""
+import pytest
+
+from tests import parity_checks as pc
+
+LIN = [n for n in pc.golden_names("lin_") if pc.is_supported(pc.golden(n))]
+RUNS = [n for n in pc.golden_names("run_") if pc.is_supported(pc.golden(n))]
+# chaotic chains: the reference does not reproduce its own cached runs either;
+# they are checked teacher-forced only
+CHAOTIC = {"run_scar_euler_exact_h50_ddp_quad_reg"}
+
+
+@pytest.mark.parametrize("name", LIN)
+def test_expansion(sim_engine, name):
+    pc.check_expansion(sim_engine, name)
+
+
+@pytest.mark.parametrize("name", LIN)
+def test_backward_rollout(sim_engine, name):
+    pc.check_backward_rollout(sim_engine, name)
+
+
+@pytest.mark.parametrize("name", RUNS)
+def test_run_teacher_forced(sim_engine, name):
+    pc.check_run_teacher_forced(sim_engine, name)
+
+
+@pytest.mark.parametrize("name", [n for n in RUNS if n not in CHAOTIC])
+def test_run_free(sim_engine, name):
+    pc.check_run_free(sim_engine, name)
