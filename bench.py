@@ -333,7 +333,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32768, help="problems per GPU")
     ap.add_argument("--iters", type=int, default=20, help="solver iterations per problem")
-    ap.add_argument("--candidates", type=int, default=1, help="line-search candidates evaluated per launch")
+    ap.add_argument("--candidates", type=int, default=32, help="max line-search candidates per problem per round")
     ap.add_argument("--cpu-procs", type=int, default=64)
     ap.add_argument("--ref-max-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")

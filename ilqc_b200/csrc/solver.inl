@@ -340,11 +340,39 @@ struct Workspace {
   size_t bytes;
 };
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+// Threads one wave of the register-heavy kernels keeps resident (256 per SM at 255 registers/thread).
+// Line-search rounds with fewer searching problems than this evaluate several candidates per problem at
+// once: the speculative candidates ride on SMs that would otherwise idle.
+inline int wave_slots() {
+#if defined(ILQC_HOSTSIM)
+  return 4096;
+#else
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cached = sms * 256;
+  }
+  return cached;
+#endif
+}
+// candidates per problem in a round with n_active searching problems (at most Lmax)
+inline int round_candidates(int n_active, int Lmax) {
+  int L = wave_slots() / (n_active > 0 ? n_active : 1);
+  return L < 1 ? 1 : (L > Lmax ? Lmax : L);
+}
+// slots the workspace must hold: n_active * round_candidates(n_active) <= max(B, wave)
+inline size_t slot_capacity(int B, int Lmax) {
+  size_t cap = (size_t)B * Lmax, wave = (size_t)wave_slots();
+  size_t s = cap < wave ? cap : wave;
+  return s < (size_t)B ? (size_t)B : s;
+}
 inline void carve(Workspace* w, char* base, const Dims& d, int H, int B, int L) {
   size_t off = 0;
   auto takeD = [&](size_t n) { double* p = (double*)(base + off); off = align_up(off + n * sizeof(double)); return p; };
   auto takeI = [&](size_t n) { int32_t* p = (int32_t*)(base + off); off = align_up(off + n * sizeof(int32_t)); return p; };
-  const size_t S = (size_t)B * L;
+  const size_t S = slot_capacity(B, L);
   w->lin = takeD((size_t)H * d.lin_stride * B);
   w->traj = takeD((size_t)(H + 1) * d.nx * B);
   w->gains = takeD((size_t)H * d.gain_stride * S);
@@ -443,7 +471,8 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
 
     // ---- line search rounds ----
     while (n_active > 0) {
-      const int n_slots = n_active * L;
+      P.L = round_candidates(n_active, L);
+      const int n_slots = n_active * P.L;
       ILQC_LAUNCH((make_slots_kernel), n_active, 256, st, P, n_active, w.list, w.s_try, w.prob, w.gslot, w.step_true,
                   w.step_roll, w.reg);
       if (a->algo_type == ILQC_ALGO_GD) {

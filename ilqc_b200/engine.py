@@ -287,7 +287,7 @@ class Engine:
         return self._workspace
 
     def solve(self, env, algo="ddp_linquad_reg", max_iter=10, x0=None, cmd0=None, stepsize=None, batch=None,
-              weights=None, t0=None, horizon=None, n_candidates=1, line_search=True, compute_grad_norm=True,
+              weights=None, t0=None, horizon=None, n_candidates=16, line_search=True, compute_grad_norm=True,
               record_trips=False, max_ls_trips=0):
         """run_min_algo for a batch of problems of one family (device tensors in / out)."""
         if cmd0 is not None:

@@ -87,7 +87,10 @@ def test_candidate_count_invariance(cuda_engine, algo):
     ref = cuda_engine.solve(env, algo, 3, x0=x0, weights=w, n_candidates=1, record_trips=True)
     for L in (3, 8):
         r = cuda_engine.solve(env, algo, 3, x0=x0, weights=w, n_candidates=L, record_trips=True)
-        assert torch.equal(r.cmd, ref.cmd) and torch.equal(r.cost, ref.cost) and torch.equal(r.stepsize, ref.stepsize)
+        # (cost rows of problems that stopped early are NaN padding: compare with NaN == NaN)
+        same = lambda a, b: torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+        assert same(r.cmd, ref.cmd) and same(r.cost, ref.cost) and same(r.stepsize, ref.stepsize)
+        assert torch.equal(r.ls_trips, ref.ls_trips) and torch.equal(r.status, ref.status)
 
 
 def test_full_size_properties(cuda_engine):
