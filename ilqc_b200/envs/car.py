@@ -14,10 +14,13 @@ from .. import _lib
 from .forward import DiffEnv
 from .tracks import get_track
 
-# envs/bicycle_model.json
+# envs/bicycle_model.json AS THE REFERENCE READS IT: pandas.read_json(typ="series") (car.py:104-106), whose
+# fast float parser is off by one ulp from the decimal literal for Cm1, Cr0, Cr2, Dr, Bf and Iz.  The digits
+# below are the doubles the reference actually computes with (tools/import_track_data.py prints them).
 BICYCLE_CONSTANTS = dict(
-    Cm1=0.287, Cm2=0.0545, Cr0=0.0518, Cr2=0.00035, Br=3.3852, Cr=1.2691, Dr=0.1737, Bf=2.579, Cf=1.2, Df=0.192,
-    m=0.041, Iz=27.8e-6, lf=0.029, lr=0.033, car_l=0.06, car_w=0.03,
+    Cm1=0.28700000000000003, Cm2=0.0545, Cr0=0.051800000000000006, Cr2=0.00035000000000000005, Br=3.3852,
+    Cr=1.2691, Dr=0.17370000000000002, Bf=2.5789999999999997, Cf=1.2, Df=0.192, m=0.041,
+    Iz=2.7799999999999998e-05, lf=0.029, lr=0.033, car_l=0.06, car_w=0.03,
 )
 
 _TIME_PENALTY = {"vref_squared": _lib.TP_VREF_SQUARED, "tref": _lib.TP_TREF, "dref": _lib.TP_DREF,

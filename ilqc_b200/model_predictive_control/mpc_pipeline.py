@@ -99,7 +99,7 @@ def run_mpc_batched(env, full_horizon: int, window_size: int, overlap: int, max_
                 x_frozen, k_frozen = traj[:, -1].contiguous(), a_pos
             r = run_min_algo_batched(env, max_iter, algo, x0=x_frozen, prev_cmd=init_cmd, weights=wts, t0=a,
                                      n_candidates=n_candidates, engine=eng)
-            cmd_hist = torch.cat((cmd_hist[:, :curr - overlap], r.cmd), dim=1)
+            cmd_hist = torch.cat((cmd_hist[:, :-overlap], r.cmd), dim=1)  # prev_cmd[:-overlap] (mpc_pipeline.py:53)
         costs.append(r.cost)
         stats.append(r.status)
         horizons.append(horizon)
