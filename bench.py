@@ -197,7 +197,7 @@ def run_ours(args):
     gathered = {}
 
     def step():
-        r = eng.solve(env, ALGO, iters, x0=x0d, weights=wd, n_candidates=L)
+        r = eng.solve(env, ALGO, iters, x0=x0d, weights=wd, n_candidates=L, scheduler=args.scheduler)
         if world > 1:  # the path's only collective: all-gather of the results
             for name, t in (("cost", r.cost), ("cmd", r.cmd), ("stepsize", r.stepsize), ("status", r.status)):
                 out = gathered.get(name)
@@ -242,7 +242,7 @@ def run_ours(args):
     def e2e_step():
         cmdh.zero_()
         steph.fill_(100.0)
-        return eng.solve_host(env, ALGO, iters, x0h, cmdh, steph, weights=wd, n_candidates=L)
+        return eng.solve_host(env, ALGO, iters, x0h, cmdh, steph, weights=wd, n_candidates=L, scheduler=args.scheduler)
 
     e2e_step()
     barrier()
@@ -299,7 +299,7 @@ def run_ours(args):
         "ms_per_step": 1e3 * elapsed_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "bicycle car RK4 H=100 dt=0.01 contouring, ddp_linquad_reg (BASELINE configs[3], per-GPU slice)",
-                   "batch_per_gpu": B, "global_batch": B * world, "solver_iterations": iters, "line_search_candidates": L,
+                   "batch_per_gpu": B, "global_batch": B * world, "solver_iterations": iters, "line_search_candidates": L, "scheduler": {0: "auto (asynchronous)", 1: "lock-step", 2: "asynchronous"}[args.scheduler],
                    "parallelism": f"dp{world} (independent slices, final all-gather only)",
                    "l2": "working set (expansion+gains, >1 GB) is far larger than the 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_tot.item() / e2e_s.item(), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -334,6 +334,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32768, help="problems per GPU")
     ap.add_argument("--iters", type=int, default=20, help="solver iterations per problem")
     ap.add_argument("--candidates", type=int, default=32, help="max line-search candidates per problem per round")
+    ap.add_argument("--scheduler", type=int, default=0, help="0 auto, 1 lock-step iterations, 2 asynchronous")
     ap.add_argument("--cpu-procs", type=int, default=64)
     ap.add_argument("--ref-max-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")

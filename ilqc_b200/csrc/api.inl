@@ -2,6 +2,7 @@
 // and the test-only host simulator (tests/hostsim/api_hostsim.cpp).
 #include "launch.cuh"
 #include "solver.inl"
+#include "solver_async.inl"
 
 namespace ilqc {
 int dense_lq_backward(int nx, int nu, int H, int B, int L, const double* A, const double* Bm, const double* p,
@@ -12,6 +13,22 @@ int dense_rollout_lin(int nx, int nu, int H, int B, int L, const double* A, cons
 }
 
 using namespace ilqc;
+
+// scheduler choice (ilqc_algo_desc.scheduler): 0 = automatic (asynchronous driver for the regularised step
+// modes and gd, lock-step driver for the direction modes), 1 = lock-step, 2 = asynchronous
+static int solve_dispatch(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const double* x0, double* cmd,
+                          double* stepsize, int n_iter, double* cost, double* gnorm, double* step_rep, int32_t* n_done,
+                          int32_t* status, int32_t* ls_trips, void* workspace, size_t workspace_bytes, stream_t st) {
+  if (!a) return ILQC_E_ARG;
+  const bool regmode = a->algo_type == ILQC_ALGO_GD || a->step_mode == ILQC_STEP_REG || a->step_mode == ILQC_STEP_REGVAR;
+  int sched = a->scheduler;
+  if (sched == 0) sched = regmode ? 2 : 1;
+  if (sched == 2)
+    return solve_async_impl(m, a, B, x0, cmd, stepsize, n_iter, cost, gnorm, step_rep, n_done, status, ls_trips,
+                            workspace, workspace_bytes, st);
+  return solve_impl(m, a, B, x0, cmd, stepsize, n_iter, cost, gnorm, step_rep, n_done, status, ls_trips, workspace,
+                    workspace_bytes, st);
+}
 
 extern "C" {
 
@@ -42,7 +59,7 @@ int ilqc_rollout_cost(const ilqc_model_desc* m, int B, const double* x0, const d
   int rc = get_dims(m, &d);
   if (rc) return rc;
   if (B <= 0 || !x0 || !cmd) return ILQC_E_ARG;
-  ILQC_FOR_MODEL(m->model, return LM::forward(0, *m, B, x0, cmd, nullptr, traj, cost_t, total, nullptr, (stream_t)stream));
+  ILQC_FOR_MODEL(m->model, return LM::forward(0, *m, B, B, nullptr, x0, cmd, nullptr, traj, cost_t, total, nullptr, (stream_t)stream));
   return 0;
 }
 
@@ -52,7 +69,7 @@ int ilqc_linearize(const ilqc_model_desc* m, int B, const double* x0, const doub
   int rc = get_dims(m, &d);
   if (rc) return rc;
   if (B <= 0 || !x0 || !cmd || !lin) return ILQC_E_ARG;
-  ILQC_FOR_MODEL(m->model, return LM::forward(1, *m, B, x0, cmd, lin, traj, nullptr, total, nullptr, (stream_t)stream));
+  ILQC_FOR_MODEL(m->model, return LM::forward(1, *m, B, B, nullptr, x0, cmd, lin, traj, nullptr, total, nullptr, (stream_t)stream));
   return 0;
 }
 
@@ -120,7 +137,7 @@ int ilqc_grad_obj(const ilqc_model_desc* m, int B, const double* lin, double* gr
   if (rc) return rc;
   if (B <= 0 || !lin || !gnorm) return ILQC_E_ARG;
   (void)cnorm;
-  ILQC_FOR_MODEL(m->model, return LM::adjoint(*m, B, lin, grad, gnorm, (stream_t)stream));
+  ILQC_FOR_MODEL(m->model, return LM::adjoint(*m, B, B, nullptr, lin, grad, gnorm, (stream_t)stream));
   return 0;
 }
 
@@ -136,8 +153,8 @@ int ilqc_solve(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const d
                double* stepsize, int n_iter, double* cost, double* gnorm, double* step_rep, int32_t* n_done,
                int32_t* status, int32_t* ls_trips, void* workspace, size_t workspace_bytes, void* stream) {
   if (!m || !a || !x0 || !cmd || !stepsize || !cost || !gnorm || !step_rep || !n_done || !status) return ILQC_E_ARG;
-  return solve_impl(m, a, B, x0, cmd, stepsize, n_iter, cost, gnorm, step_rep, n_done, status, ls_trips, workspace,
-                    workspace_bytes, (stream_t)stream);
+  return solve_dispatch(m, a, B, x0, cmd, stepsize, n_iter, cost, gnorm, step_rep, n_done, status, ls_trips, workspace,
+                        workspace_bytes, (stream_t)stream);
 }
 
 // per-kernel-class CUDA-event timing of ilqc_solve (classes: 0 roll-out+cost, 1 expansion, 2 backward,
@@ -205,8 +222,8 @@ int ilqc_solve_host(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, co
   ILQC_CHECK(dev_h2d(step_d, stepsize_host, sizeof(double) * B, st));
   ILQC_CHECK(ilqc_to_soa(x0_aos, x0_soa, B, d.nx, stream));
   ILQC_CHECK(ilqc_to_soa(cmd_aos, cmd_soa, B, H * d.nu, stream));
-  ILQC_CHECK(solve_impl(m, a, B, x0_soa, cmd_soa, step_d, n_iter, met_soa, met_soa + mrows, met_soa + 2 * mrows,
-                        n_done_d, status_d, nullptr, workspace, ws, st));
+  ILQC_CHECK(solve_dispatch(m, a, B, x0_soa, cmd_soa, step_d, n_iter, met_soa, met_soa + mrows, met_soa + 2 * mrows,
+                            n_done_d, status_d, nullptr, workspace, ws, st));
   ILQC_CHECK(ilqc_from_soa(cmd_soa, cmd_aos, B, H * d.nu, stream));
   for (int k = 0; k < 3; ++k) ILQC_CHECK(ilqc_from_soa(met_soa + k * mrows, met_aos + k * mrows, B, n_iter + 1, stream));
   ILQC_CHECK(dev_d2h(cmd_host, cmd_aos, sizeof(double) * B * H * d.nu, st));

@@ -17,6 +17,7 @@ extern thread_local int g_sim_tid;
 typedef void* stream_t;
 }
 #define ILQC_GLOBAL static void
+#define ILQC_GLOBAL_LB(minblocks) static void
 #define ILQC_TID (::ilqc::g_sim_tid)
 #define ILQC_UNPAREN(...) __VA_ARGS__
 #define ILQC_LAUNCH(kern, n, block, stream, ...)                 \
@@ -33,6 +34,7 @@ namespace ilqc {
 typedef cudaStream_t stream_t;
 }
 #define ILQC_GLOBAL __global__ void
+#define ILQC_GLOBAL_LB(minblocks) __global__ void __launch_bounds__(ILQC_BLOCK, minblocks)
 #define ILQC_TID ((int)(blockIdx.x * blockDim.x + threadIdx.x))
 #define ILQC_UNPAREN(...) __VA_ARGS__
 #define ILQC_LAUNCH(kern, n, block, stream, ...)                                                   \
@@ -46,14 +48,31 @@ namespace ilqc {
 
 // thread-block size of the thread-per-problem kernels.  The big bodies use ~255 registers, so an SM holds
 // 256 threads; small blocks keep all 148 SMs busy for batches that are not a multiple of 148*256.
-constexpr int kBlock = 64;
+#ifndef ILQC_BLOCK
+#define ILQC_BLOCK 64
+#endif
+constexpr int kBlock = ILQC_BLOCK;
+// Occupancy targets (resident blocks per SM) of the three heavy kernel families; they set the register
+// budget ptxas works with: 65536 / (ILQC_BLOCK * blocks) registers per thread.  Tuned on a B200 with
+// tools/tune_kernels.py (profiles/r01_tuning.txt).
+#ifndef ILQC_LB_FWD1
+#define ILQC_LB_FWD1 4
+#endif
+#ifndef ILQC_LB_BWD
+#define ILQC_LB_BWD 4
+#endif
+#ifndef ILQC_LB_ROLL
+#define ILQC_LB_ROLL 8
+#endif
 
 // Per-model launchers, defined once per model in model_kernels.inl (one translation unit per model so
 // that the heavy templates compile in parallel).
 template <int MODEL>
 struct Launch {
-  static int forward(int order, const ilqc_model_desc& m, int B, const double* x0, const double* cmd,
-                     double* lin, double* traj, double* cost_t, double* total, double* cnorm, stream_t st);
+  // n_threads threads; thread a serves problem prob[a] (prob == NULL: a, n_threads == B)
+  static int forward(int order, const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob,
+                     const double* x0, const double* cmd, double* lin, double* traj, double* cost_t, double* total,
+                     double* cnorm, stream_t st);
   static int expand_dense(const ilqc_model_desc& m, int B, const double* x0, const double* cmd, int order,
                           double* A, double* Bm, double* p, double* P, double* q, double* Q, const double* lam,
                           double* Hxx, double* Hxu, double* Huu, stream_t st);
@@ -69,8 +88,8 @@ struct Launch {
                      const double* x0, const double* cmd, const double* traj, const double* lin,
                      const double* gains, const double* dir, double* diff, double* newval, double* diffsq,
                      stream_t st);
-  static int adjoint(const ilqc_model_desc& m, int B, const double* lin, double* grad, double* gnorm,
-                     stream_t st);
+  static int adjoint(const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob, const double* lin,
+                     double* grad, double* gnorm, stream_t st);
   static void dims(int* nx, int* nu, int* lin_stride, int* gain_stride);
 };
 

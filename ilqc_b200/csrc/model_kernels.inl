@@ -13,15 +13,17 @@ namespace {
 using MI = Model<ILQC_MODEL_INST>;
 
 template <class M, int ORD>
-ILQC_GLOBAL forward_kernel(ilqc_model_desc m, int B, const double* x0, const double* cmd, double* lin,
-                           double* traj, double* cost_t, double* total, double* cnorm) {
-  const int b = ILQC_TID;
-  if (b >= B) return;
+ILQC_GLOBAL_LB(ILQC_LB_FWD1) forward_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const double* x0,
+                                            const double* cmd, double* lin, double* traj, double* cost_t, double* total,
+                                            double* cnorm) {
+  const int a = ILQC_TID;
+  if (a >= n_threads) return;
+  const int b = prob ? prob[a] : a;
   forward_body<M, ORD>(m, b, B, x0, cmd, lin, traj, cost_t, total, cnorm);
 }
 
 template <class M, int MODE>
-ILQC_GLOBAL backward_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const int32_t* oslot,
+ILQC_GLOBAL_LB(ILQC_LB_BWD) backward_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const int32_t* oslot,
                             int n_oslots, const double* reg_ctrl, double reg_state, const double* lin,
                             const double* traj, const double* cmd, double* gains, double* jcst, int32_t* feasible) {
   const int s = ILQC_TID;
@@ -32,7 +34,7 @@ ILQC_GLOBAL backward_kernel(ilqc_model_desc m, int B, int n_threads, const int32
 }
 
 template <class M, int KIND>
-ILQC_GLOBAL rollout_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const int32_t* gslot,
+ILQC_GLOBAL_LB(ILQC_LB_ROLL) rollout_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const int32_t* gslot,
                            int n_gslots, const int32_t* oslot, int n_oslots, const double* step, const double* x0,
                            const double* cmd, const double* traj, const double* lin, const double* gains,
                            const double* dir, double* diff, double* newval, double* diffsq) {
@@ -46,9 +48,11 @@ ILQC_GLOBAL rollout_kernel(ilqc_model_desc m, int B, int n_threads, const int32_
 }
 
 template <class M>
-ILQC_GLOBAL adjoint_kernel(ilqc_model_desc m, int B, const double* lin, double* grad, double* gnorm) {
-  const int b = ILQC_TID;
-  if (b >= B) return;
+ILQC_GLOBAL adjoint_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const double* lin,
+                           double* grad, double* gnorm) {
+  const int a = ILQC_TID;
+  if (a >= n_threads) return;
+  const int b = prob ? prob[a] : a;
   adjoint_body<M>(m, b, B, lin, grad, gnorm);
 }
 
@@ -148,11 +152,13 @@ ILQC_GLOBAL expand_dense_kernel(ilqc_model_desc m, int B, const double* x0, cons
 }  // namespace
 
 template <>
-int Launch<ILQC_MODEL_INST>::forward(int order, const ilqc_model_desc& m, int B, const double* x0,
-                                     const double* cmd, double* lin, double* traj, double* cost_t, double* total,
-                                     double* cnorm, stream_t st) {
-  if (order == 0) ILQC_LAUNCH((forward_kernel<MI, 0>), B, kBlock, st, m, B, x0, cmd, lin, traj, cost_t, total, cnorm);
-  else ILQC_LAUNCH((forward_kernel<MI, 1>), B, kBlock, st, m, B, x0, cmd, lin, traj, cost_t, total, cnorm);
+int Launch<ILQC_MODEL_INST>::forward(int order, const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob,
+                                     const double* x0, const double* cmd, double* lin, double* traj, double* cost_t,
+                                     double* total, double* cnorm, stream_t st) {
+  if (order == 0)
+    ILQC_LAUNCH((forward_kernel<MI, 0>), n_threads, kBlock, st, m, B, n_threads, prob, x0, cmd, lin, traj, cost_t, total, cnorm);
+  else
+    ILQC_LAUNCH((forward_kernel<MI, 1>), n_threads, kBlock, st, m, B, n_threads, prob, x0, cmd, lin, traj, cost_t, total, cnorm);
   return ILQC_LAUNCH_OK();
 }
 
@@ -205,9 +211,9 @@ int Launch<ILQC_MODEL_INST>::rollout(int kind, const ilqc_model_desc& m, int B, 
 }
 
 template <>
-int Launch<ILQC_MODEL_INST>::adjoint(const ilqc_model_desc& m, int B, const double* lin, double* grad,
-                                     double* gnorm, stream_t st) {
-  ILQC_LAUNCH((adjoint_kernel<MI>), B, kBlock, st, m, B, lin, grad, gnorm);
+int Launch<ILQC_MODEL_INST>::adjoint(const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob,
+                                     const double* lin, double* grad, double* gnorm, stream_t st) {
+  ILQC_LAUNCH((adjoint_kernel<MI>), n_threads, kBlock, st, m, B, n_threads, prob, lin, grad, gnorm);
   return ILQC_LAUNCH_OK();
 }
 

@@ -148,6 +148,7 @@ struct Bell {
       for (int c = 0; c < NX; ++c) rhs[u][c] = G[u][c];
       rhs[u][NX] = gq[u];
     }
+    double ipiv[NU];
 #pragma unroll
     for (int c = 0; c < NU; ++c) {
 #pragma unroll
@@ -166,10 +167,12 @@ struct Bell {
           rhs[r][cc] = sw ? a : b;
         }
       }
-      const double piv = Hm[c][c];
+      // one reciprocal per pivot (an FP64 division is ~25 instructions; the NX+1 right-hand sides would
+      // otherwise pay it NU*(NX+1) times per step)
+      ipiv[c] = 1.0 / Hm[c][c];
 #pragma unroll
       for (int r = c + 1; r < NU; ++r) {
-        const double f = Hm[r][c] / piv;
+        const double f = Hm[r][c] * ipiv[c];
 #pragma unroll
         for (int cc = c + 1; cc < NU; ++cc) Hm[r][cc] -= f * Hm[c][cc];
 #pragma unroll
@@ -183,7 +186,7 @@ struct Bell {
         double acc = rhs[r][cc];
 #pragma unroll
         for (int c2 = r + 1; c2 < NU; ++c2) acc -= Hm[r][c2] * rhs[c2][cc];
-        rhs[r][cc] = acc / Hm[r][r];
+        rhs[r][cc] = acc * ipiv[r];
       }
     }
 #pragma unroll

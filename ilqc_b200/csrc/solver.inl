@@ -16,6 +16,7 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "launch.cuh"
 
@@ -68,7 +69,7 @@ struct ProfState {
 };
 inline ProfState& prof_state() { static ProfState s; return s; }
 #if defined(ILQC_HOSTSIM)
-struct ProfScope { ProfScope(stream_t) {} void begin(int, long long) {} void end() {} void flush() {} };
+struct ProfScope { ProfScope(stream_t) {} void begin(int, long long) {} void begin_on(int, long long, stream_t) {} void end() {} void flush() {} };
 #else
 struct ProfScope {
   struct Rec { int cls; long long units; cudaEvent_t e0, e1; };
@@ -76,14 +77,17 @@ struct ProfScope {
   stream_t st;
   bool on;
   explicit ProfScope(stream_t s) : st(s), on(prof_state().enabled != 0) {}
-  void begin(int cls, long long units) {
+  stream_t cur;
+  void begin(int cls, long long units) { begin_on(cls, units, st); }
+  void begin_on(int cls, long long units, stream_t s) {
     if (!on) return;
     Rec r; r.cls = cls; r.units = units;
     cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
-    cudaEventRecord(r.e0, st);
+    cur = s;
+    cudaEventRecord(r.e0, s);
     recs.push_back(r);
   }
-  void end() { if (on) cudaEventRecord(recs.back().e1, st); }
+  void end() { if (on) cudaEventRecord(recs.back().e1, cur); }
   void flush() {  // call after the stream has been synchronised
     for (auto& r : recs) {
       float ms = 0.f;
@@ -96,6 +100,7 @@ struct ProfScope {
 };
 #endif
 #define ILQC_PROF(cls, units, stmt) do { prof.begin(cls, units); stmt; prof.end(); } while (0)
+#define ILQC_PROF_ON(stream, cls, units, stmt) do { prof.begin_on(cls, units, stream); stmt; prof.end(); } while (0)
 
 struct Dims { int nx, nu, lin_stride, gain_stride; };
 inline int get_dims(const ilqc_model_desc* m, Dims* d) {
@@ -115,6 +120,12 @@ struct LsParams {
   int algo_type, approx, step_mode, L, line_search, H, nu;
   double rho;
 };
+// per-problem scheduler state of the asynchronous driver (all NULL in the lock-step driver)
+enum { PHASE_LIN = 0, PHASE_LS = 1, PHASE_DONE = 2 };
+struct AsyncState {
+  int32_t *phase, *iter, *ls_trips, *n_done;
+  double *cost, *gn, *step_rep;
+};
 
 // min_step's line-search set-up (algos_steps.py:333-367): first trial step of every running problem
 ILQC_GLOBAL ls_init_kernel(LsParams P, int B, const int32_t* status, const double* stepsize, const double* cnorm,
@@ -131,8 +142,8 @@ ILQC_GLOBAL ls_init_kernel(LsParams P, int B, const int32_t* status, const doubl
       else s = ::fmin(4.0 * s, 1.0);
     }
     s_try[b] = s;
-    trips[b] = 0;
   }
+  trips[b] = 0;  // (stopped problems report 0 trips for the iterations they no longer run)
   flags[b] = act;
 }
 
@@ -200,9 +211,9 @@ ILQC_GLOBAL make_slots_kernel(LsParams P, int n_active, const int32_t* list, con
 ILQC_GLOBAL ls_select_kernel(LsParams P, int n_active, int B, int n_slots, const int32_t* list,
                              const double* step_true, const double* newval, const double* diffsq,
                              const double* jcst_slot, const double* dec_unit, const int32_t* feas_slot,
-                             const int32_t* feas_prob, const double* diff, const double* cnorm, double* cmd,
-                             double* curr_val, double* stepsize, double* s_try, int32_t* status, int32_t* flags,
-                             int32_t* trips, int max_trips) {
+                             const int32_t* feas_prob, const double* cnorm, double* curr_val, double* stepsize,
+                             double* s_try, int32_t* status, int32_t* flags, int32_t* trips, int32_t* accept,
+                             int max_trips, AsyncState A) {
   const int a = ILQC_TID;
   if (a >= n_active) return;
   const int b = list[a];
@@ -235,25 +246,124 @@ ILQC_GLOBAL ls_select_kernel(LsParams P, int n_active, int B, int n_slots, const
     }
   }
   trips[b] = ntrip;
+  accept[a] = -1;
   if (chosen >= 0) {
     const int slot = a * P.L + chosen;
     if (chosen_feasible) {
-      const int n = P.H * P.nu;
-      for (int e = 0; e < n; ++e) cmd[(size_t)e * B + b] += diff[(size_t)e * n_slots + slot];
+      accept[a] = slot;  // cmd += diff[slot] is done by apply_kernel, coalesced over the active problems
       curr_val[b] = newval[slot];
       if (P.line_search) {
         const double s = step_true[slot];
         stepsize[b] = (P.step_mode == ILQC_STEP_REG && P.algo_type != ILQC_ALGO_GD) ? s * cnorm[b] : s;
       }
+      if (A.phase) {  // asynchronous scheduler: this problem moves on to its re-expansion
+        const int it = A.iter[b];
+        if (A.ls_trips) A.ls_trips[(size_t)it * B + b] = ntrip;
+        A.iter[b] = it + 1;
+        A.phase[b] = PHASE_LIN;
+      }
     } else {
       status[b] = ILQC_NO_DIRECTION;  // min_step returns None (algos_steps.py:379-380)
       curr_val[b] = NAN;
+      if (A.phase) {
+        const int it = A.iter[b];
+        if (A.ls_trips) A.ls_trips[(size_t)it * B + b] = ntrip;
+        const size_t row = (size_t)(it + 1) * B + b;  // collect_info with costs=None: NaN cost once
+        A.cost[row] = NAN; A.gn[row] = NAN; A.step_rep[row] = stepsize[b];
+        A.n_done[b] = it + 1;
+        A.phase[b] = PHASE_DONE;
+      }
     }
     flags[b] = 0;
   } else {
     s_try[b] = step_true[a * P.L + P.L - 1] * P.rho;
     flags[b] = 1;
   }
+}
+
+// ordered compaction of the problems with phase[b] == value (asynchronous scheduler)
+#if defined(ILQC_HOSTSIM)
+ILQC_GLOBAL compact_eq_kernel(int B, const int32_t* phase, int value, int32_t* list, int32_t* count) {
+  int n = 0;
+  for (int b = 0; b < B; ++b)
+    if (phase[b] == value) list[n++] = b;
+  *count = n;
+}
+#else
+__global__ void compact_eq_kernel(int B, const int32_t* phase, int value, int32_t* list, int32_t* count) {
+  __shared__ int sums[1024];
+  const int tid = threadIdx.x;
+  const int chunk = (B + 1023) / 1024;
+  const int lo = tid * chunk, hi = min(B, lo + chunk);
+  int n = 0;
+  for (int b = lo; b < hi; ++b) n += phase[b] == value;
+  sums[tid] = n;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int v = (tid >= off) ? sums[tid - off] : 0;
+    __syncthreads();
+    sums[tid] += v;
+    __syncthreads();
+  }
+  int pos = sums[tid] - n;
+  for (int b = lo; b < hi; ++b)
+    if (phase[b] == value) list[pos++] = b;
+  if (tid == 1023) *count = sums[1023];
+}
+#endif
+
+// asynchronous scheduler: collect_info + check_cvg_status for the problems that were just re-expanded, each
+// at its own iteration index, followed by the line-search set-up of its next iteration (ls_init_kernel)
+ILQC_GLOBAL status_async_kernel(LsParams P, int n_list, const int32_t* list, int B, int n_iter, const double* curr_val,
+                                const double* gnorm, const double* cnorm, const double* stepsize, double* s_try,
+                                double* dec_unit, int32_t* trips, int32_t* status, AsyncState A) {
+  const int a = ILQC_TID;
+  if (a >= n_list) return;
+  const int b = list[a];
+  const int it = A.iter[b];
+  const size_t row = (size_t)it * B + b;
+  const double c = curr_val[b];
+  double srep = stepsize[b];
+  if (P.algo_type != ILQC_ALGO_GD && P.step_mode == ILQC_STEP_REG && it > 0) srep = srep * A.gn[(size_t)(it - 1) * B + b];
+  A.cost[row] = c;
+  A.gn[row] = gnorm[b];
+  A.step_rep[row] = srep;
+  A.n_done[b] = it;
+  int st = ILQC_RUNNING;
+  const double c0 = A.cost[b];
+  if (c != c || c > c0 + 1e3) st = ILQC_DIVERGED;
+  if (it > 0) {
+    const double cp = A.cost[(size_t)(it - 1) * B + b];
+    if (::fabs(c - cp) / ::fabs(cp) < 1e-24) st = ILQC_CONVERGED;
+  }
+  if (st == ILQC_RUNNING && srep < 1e-24) st = ILQC_STUCK;
+  status[b] = st;
+  if (st == ILQC_RUNNING && it < n_iter) {
+    double s = stepsize[b];
+    if (P.line_search) {
+      if (P.step_mode == ILQC_STEP_DIR) s = 1.0;
+      else if (P.step_mode == ILQC_STEP_REG) s = (8.0 * s) / cnorm[b];
+      else if (P.step_mode == ILQC_STEP_REGVAR) s = s * 8.0;
+      else s = ::fmin(4.0 * s, 1.0);
+    }
+    s_try[b] = s;
+    trips[b] = 0;
+    if (P.algo_type == ILQC_ALGO_GD) dec_unit[b] = -0.5 * (gnorm[b] * gnorm[b]);
+    A.phase[b] = PHASE_LS;
+  } else {
+    A.phase[b] = PHASE_DONE;
+  }
+}
+
+// next_cmd = cmd + diff_cmd (algos_steps.py:377) for the problems whose line search just ended: thread
+// (a, e) with the active index a fastest, so both the candidate read and the cmd write are coalesced
+ILQC_GLOBAL apply_kernel(int n_active, int n_elem, int B, int n_slots, const int32_t* list, const int32_t* accept,
+                         const double* diff, double* cmd) {
+  const int i = ILQC_TID;
+  if (i >= n_active * n_elem) return;
+  const int a = i % n_active, e = i / n_active;
+  const int slot = accept[a];
+  if (slot >= 0) cmd[(size_t)e * B + list[a]] += diff[(size_t)e * n_slots + slot];
 }
 
 // collect_info + check_cvg_status (run_min_algo.py:127-264) for metrics row `it`
@@ -336,13 +446,18 @@ ILQC_GLOBAL from_soa_kernel(const double* src, double* dst, int B, int n) {
 struct Workspace {
   double *lin, *traj, *gains, *diff, *dir, *newval, *diffsq, *jcst, *step_true, *step_roll, *reg, *curr_val,
       *cnorm, *gnorm, *s_try, *dec_unit, *reg_prob;
-  int32_t *prob, *gslot, *feas_slot, *feas_prob, *list, *flags, *trips, *count, *ident;
+  int32_t *prob, *gslot, *feas_slot, *feas_prob, *list, *flags, *trips, *count, *ident, *accept, *phase, *iter;
   size_t bytes;
 };
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 // Threads one wave of the register-heavy kernels keeps resident (256 per SM at 255 registers/thread).
 // Line-search rounds with fewer searching problems than this evaluate several candidates per problem at
 // once: the speculative candidates ride on SMs that would otherwise idle.
+// 640 threads per SM (= one full wave of the roll-out kernel at 100 registers, 2.5 waves of the backward
+// kernel) measured best on the bicycle workload: profiles/r01_tuning_scheduler.txt
+#ifndef ILQC_WAVE_THREADS_PER_SM
+#define ILQC_WAVE_THREADS_PER_SM 640
+#endif
 inline int wave_slots() {
 #if defined(ILQC_HOSTSIM)
   return 4096;
@@ -352,7 +467,11 @@ inline int wave_slots() {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cached = sms * 256;
+    cached = sms * ILQC_WAVE_THREADS_PER_SM;
+    if (const char* e = getenv("ILQC_WAVE_SLOTS")) {  // tuning knob (tools/gpu_tune.sh)
+      const int v = atoi(e);
+      if (v > 0) cached = v;
+    }
   }
   return cached;
 #endif
@@ -383,7 +502,8 @@ inline void carve(Workspace* w, char* base, const Dims& d, int H, int B, int L) 
   w->curr_val = takeD(B); w->cnorm = takeD(B); w->gnorm = takeD(B); w->s_try = takeD(B); w->dec_unit = takeD(B);
   w->reg_prob = takeD(B);
   w->prob = takeI(S); w->gslot = takeI(S); w->feas_slot = takeI(S);
-  w->feas_prob = takeI(B); w->list = takeI(B); w->flags = takeI(B); w->trips = takeI(B); w->ident = takeI(B);
+  w->feas_prob = takeI(B); w->list = takeI(B); w->flags = takeI(B); w->trips = takeI(B); w->ident = takeI(B); w->accept = takeI(B);
+  w->phase = takeI(B); w->iter = takeI(B);
   w->count = takeI(64);
   w->bytes = off;
 }
@@ -424,9 +544,9 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
 
   // iteration 0: objective of the initial controls (same arithmetic as every candidate evaluation), its
   // expansion and the metrics row 0 (run_min_algo.py:65-76)
-  ILQC_PROF(PROF_FORWARD0, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(0, md, B, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st))));
-  ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
-  if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, w.lin, w.dir, w.gnorm, st))));
+  ILQC_PROF(PROF_FORWARD0, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(0, md, B, B, nullptr, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st))));
+  ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
+  if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
   ILQC_LAUNCH((status_kernel), B, 256, st, P, B, 0, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
               n_done);
 
@@ -492,16 +612,17 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
                                                         w.traj, w.lin, w.gains, w.dir, w.diff, w.newval, w.diffsq, st))));
       }
       ILQC_LAUNCH((ls_select_kernel), n_active, 128, st, P, n_active, B, n_slots, w.list, w.step_true, w.newval, w.diffsq,
-                  w.jcst, w.dec_unit, w.feas_slot, w.feas_prob, w.diff, w.cnorm, cmd, w.curr_val, stepsize, w.s_try,
-                  status, w.flags, w.trips, max_trips);
+                  w.jcst, w.dec_unit, w.feas_slot, w.feas_prob, w.cnorm, w.curr_val, stepsize, w.s_try, status, w.flags,
+                  w.trips, w.accept, max_trips, AsyncState{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr});
+      ILQC_LAUNCH((apply_kernel), n_active * (H * d.nu), 256, st, n_active, H * d.nu, B, n_slots, w.list, w.accept, w.diff, cmd);
       ILQC_LAUNCH((compact_kernel), 1, 1024, st, B, w.flags, w.list, w.count);
       ILQC_CHECK(dev_d2h_sync(&n_active, w.count, sizeof(int), st));
     }
     if (ls_trips) ILQC_CHECK(dev_d2d(ls_trips + (size_t)(it - 1) * B, w.trips, sizeof(int32_t) * B, st));
 
     // re-expand at the accepted controls (algos_steps.py:376-378) and collect the metrics of this iteration
-    ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
-    if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, w.lin, w.dir, w.gnorm, st))));
+    ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
+    if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
     ILQC_LAUNCH((status_kernel), B, 256, st, P, B, it, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
                 n_done);
   }

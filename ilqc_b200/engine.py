@@ -271,13 +271,14 @@ class Engine:
         return diff.reshape(H, nu, B, L).permute(2, 3, 0, 1).contiguous()
 
     # ---- run_min_algo -------------------------------------------------------------------------------------
-    def algo_desc(self, algo, n_candidates=1, line_search=True, compute_grad_norm=True, max_ls_trips=0):
+    def algo_desc(self, algo, n_candidates=1, line_search=True, compute_grad_norm=True, max_ls_trips=0, scheduler=0):
         a = _lib.AlgoDesc()
         a.algo_type, a.approx, a.step_mode = parse_algo(algo)
         a.n_candidates = int(n_candidates)
         a.line_search = int(bool(line_search))
         a.compute_grad_norm = int(bool(compute_grad_norm))
         a.max_ls_trips = int(max_ls_trips)
+        a.scheduler = int(scheduler)
         return a
 
     def workspace(self, nbytes):
@@ -288,7 +289,7 @@ class Engine:
 
     def solve(self, env, algo="ddp_linquad_reg", max_iter=10, x0=None, cmd0=None, stepsize=None, batch=None,
               weights=None, t0=None, horizon=None, n_candidates=16, line_search=True, compute_grad_norm=True,
-              record_trips=False, max_ls_trips=0):
+              record_trips=False, max_ls_trips=0, scheduler=0):
         """run_min_algo for a batch of problems of one family (device tensors in / out)."""
         if cmd0 is not None:
             cmd0 = self._dev(cmd0)
@@ -299,7 +300,7 @@ class Engine:
         x0 = self._x0(env, x0, B).reshape(B, -1)
         d, keep = self.make_desc(env, H, B, t0, weights)
         nx, nu = self.dims(d)
-        a = self.algo_desc(algo, n_candidates, line_search, compute_grad_norm, max_ls_trips)
+        a = self.algo_desc(algo, n_candidates, line_search, compute_grad_norm, max_ls_trips, scheduler)
         cmds = self.to_soa(cmd0) if cmd0 is not None else torch.zeros(H * nu, B, dtype=F64, device=self.device)
         if stepsize is None:
             stepsize = default_stepsize(algo)
@@ -322,11 +323,11 @@ class Engine:
                            ls_trips=trips[:max_iter].t().contiguous() if record_trips else None)
 
     def solve_host(self, env, algo, max_iter, x0_host, cmd_host, stepsize_host, weights=None, t0=None,
-                   n_candidates=1, compute_grad_norm=True):
+                   n_candidates=16, compute_grad_norm=True, scheduler=0):
         """Same solve through ilqc_solve_host: HOST (pinned) tensors in the reference layout, copies inside."""
         B, H, nu = cmd_host.shape
         d, keep = self.make_desc(env, H, B, t0, weights)
-        a = self.algo_desc(algo, n_candidates, True, compute_grad_norm)
+        a = self.algo_desc(algo, n_candidates, True, compute_grad_norm, 0, scheduler)
         n = max_iter + 1
         pin = self.device.type == "cuda"
         cost = torch.empty(B, n, dtype=F64, pin_memory=pin)

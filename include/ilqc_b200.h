@@ -88,7 +88,8 @@ typedef struct ilqc_algo_desc {
   int32_t line_search;      /* run_min_algo(line_search=...) ; 0 = fixed stepsize */
   int32_t max_ls_trips;     /* safety cap on line-search trips (reference: unbounded, stops at 1e-32) */
   int32_t compute_grad_norm;/* collect_info's ||grad_u f|| each iteration (run_min_algo.py:156-157) */
-  int32_t reserved;
+  int32_t scheduler;        /* 0 auto, 1 lock-step iterations, 2 asynchronous per-problem state machines
+                               (regularised step modes and gd only); identical results either way */
 } ilqc_algo_desc;
 
 int ilqc_abi_version(void);
