@@ -14,15 +14,18 @@ int dense_rollout_lin(int nx, int nu, int H, int B, int L, const double* A, cons
 
 using namespace ilqc;
 
-// scheduler choice (ilqc_algo_desc.scheduler): 0 = automatic (asynchronous driver for the regularised step
-// modes and gd, lock-step driver for the direction modes), 1 = lock-step, 2 = asynchronous
+// scheduler choice (ilqc_algo_desc.scheduler): 0 = automatic, 1 = lock-step iterations, 2 = asynchronous
+// per-problem state machines on two streams (regularised step modes and gd only).  Both give bit-identical
+// results; on a B200 they are within noise of each other once the speculation capacity is tuned
+// (profiles/r01_tuning_scheduler.txt), so automatic = the simpler lock-step driver.
 static int solve_dispatch(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const double* x0, double* cmd,
                           double* stepsize, int n_iter, double* cost, double* gnorm, double* step_rep, int32_t* n_done,
                           int32_t* status, int32_t* ls_trips, void* workspace, size_t workspace_bytes, stream_t st) {
   if (!a) return ILQC_E_ARG;
   const bool regmode = a->algo_type == ILQC_ALGO_GD || a->step_mode == ILQC_STEP_REG || a->step_mode == ILQC_STEP_REGVAR;
   int sched = a->scheduler;
-  if (sched == 0) sched = regmode ? 2 : 1;
+  (void)regmode;
+  if (sched == 0) sched = 1;
   if (sched == 2)
     return solve_async_impl(m, a, B, x0, cmd, stepsize, n_iter, cost, gnorm, step_rep, n_done, status, ls_trips,
                             workspace, workspace_bytes, st);
@@ -168,6 +171,12 @@ int ilqc_profile_read(double* ms, int64_t* launches, int64_t* units, int n) {
     p.ms[i] = 0; p.launches[i] = 0; p.units[i] = 0;
   }
   return PROF_N;
+}
+
+long long ilqc_launch_count(int reset) {
+  const long long n = launch_counter();
+  if (reset) launch_counter() = 0;
+  return n;
 }
 
 int ilqc_to_soa(const double* src, double* dst, int B, int n, void* stream) {

@@ -201,23 +201,6 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
   for (int t = H - 1; t >= 0; --t) {
     const double* rec = lin + (size_t)t * L::stride * B + b;
     load_dyn<M>(bl, rec, B);
-    double pc[NX], Pc[NX][NX];
-    if (t > 0) {
-      load_state_cost<M>(pc, Pc, lin + (size_t)(t - 1) * L::stride * B + b, B);
-    } else {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        pc[i] = 0.0;
-#pragma unroll
-        for (int c = i; c < NX; ++c) Pc[i][c] = 0.0;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      bl.p[i] = pc[i];
-#pragma unroll
-      for (int c = i; c < NX; ++c) bl.P[i][c] = Pc[i][c];
-    }
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       bl.q[u] = rec[(size_t)(L::oq + u) * B];
@@ -225,10 +208,8 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
       for (int v = u; v < NU; ++v) bl.Q[u][v] = 0.0;
       bl.Q[u][u] = rec[(size_t)(L::oQ + u) * B] + reg_ctrl;
     }
-    if constexpr (!QUAD) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) bl.P[i][i] += reg_state;
-    } else {
+    double hxx[QUAD ? sym_size(M::NV) : 1];  // state block of the dynamics Hessian, added to P in phase 2
+    if constexpr (QUAD) {
       // Hessian of lam^T phi at (x_t, u_t) (forward.py:218-269) by second-order jets
       using S = Jet<M::NV, 2>;
       double x[NX], u[NU];
@@ -240,27 +221,19 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
       static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], M::sv(I)); });
       static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], M::uv(I)); });
       M::template step<S>(m, xs, us, xns);
-      double hl[sym_size(M::NV)];
 #pragma unroll
       for (int e = 0; e < sym_size(M::NV); ++e) {
         double acc = 0.0;
 #pragma unroll
         for (int i = 0; i < NX; ++i) acc += lam[i] * xns[i].h[e];
-        hl[e] = acc;
+        hxx[e] = acc;
       }
       static_for<NX>([&](auto I) {
         constexpr int i = I;
         if constexpr (M::sv(i) >= 0) {
-          static_for<NX>([&](auto Jc) {
-            constexpr int c = Jc;
-            if constexpr (c >= i && M::sv(c) >= 0) {
-              // P gets the state block only for t>0 (backward.py:102-108)
-              if (t > 0) bl.P[i][c] += hl[sym_idx(M::sv(i), M::sv(c), M::NV)];
-            }
-          });
           static_for<NU>([&](auto Kc) {
             constexpr int k = Kc;
-            if constexpr (M::uv(k) >= 0) bl.R[i][k] = hl[sym_idx(M::sv(i), M::uv(k), M::NV)];
+            if constexpr (M::uv(k) >= 0) bl.R[i][k] = hxx[sym_idx(M::sv(i), M::uv(k), M::NV)];
           });
         }
       });
@@ -269,21 +242,18 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
         if constexpr (M::uv(u1) >= 0) {
           static_for<NU>([&](auto V) {
             constexpr int v1 = V;
-            if constexpr (v1 >= u1 && M::uv(v1) >= 0) bl.Q[u1][v1] += hl[sym_idx(M::uv(u1), M::uv(v1), M::NV)];
+            if constexpr (v1 >= u1 && M::uv(v1) >= 0) bl.Q[u1][v1] += hxx[sym_idx(M::uv(u1), M::uv(v1), M::NV)];
           });
         }
       });
-      if (t > 0) {
-#pragma unroll
-        for (int i = 0; i < NX; ++i) bl.P[i][i] += reg_state;
-      }
     }
-    // newton-mode costate uses j-independent recursion lam <- p + A^T lam (backward.py:122-123)
+    // newton-mode costate: lam <- p + A^T lam = p + lam + N^T lam (backward.py:122-123); the N part now,
+    // p once the state cost has been loaded
     double lam_next[NX];
     if constexpr (MODE == ILQC_BWD_QUAD_NEWTON) {
       static_for<NX>([&](auto I) {
         constexpr int i = I;
-        double acc = pc[i] + lam[i];
+        double acc = lam[i];
         static_for<NX>([&](auto Rr) {
           constexpr int r = Rr;
           if constexpr (M::Nm(r, i)) acc += bl.N[r][i] * lam[r];
@@ -291,7 +261,42 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
         lam_next[i] = acc;
       });
     }
-    const double rest = bl.step(J, j);
+    bl.phase1(J, j);
+    // state cost on x_t (costs[t] of the reference; zero at t = 0), loaded only now to keep N, B, W and the
+    // cost operands from being live at the same time
+    if (t > 0) {
+      load_state_cost<M>(bl.p, bl.P, lin + (size_t)(t - 1) * L::stride * B + b, B);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        bl.p[i] = 0.0;
+#pragma unroll
+        for (int c = i; c < NX; ++c) bl.P[i][c] = 0.0;
+      }
+    }
+    if constexpr (MODE == ILQC_BWD_QUAD_NEWTON) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) lam_next[i] += bl.p[i];
+    }
+    if constexpr (!QUAD) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) bl.P[i][i] += reg_state;
+    } else {
+      if (t > 0) {  // P gets the state block of the dynamics Hessian and reg_state only for t>0 (backward.py:102-108)
+        static_for<NX>([&](auto I) {
+          constexpr int i = I;
+          if constexpr (M::sv(i) >= 0) {
+            static_for<NX>([&](auto Jc) {
+              constexpr int c = Jc;
+              if constexpr (c >= i && M::sv(c) >= 0) bl.P[i][c] += hxx[sym_idx(M::sv(i), M::sv(c), M::NV)];
+            });
+          }
+        });
+#pragma unroll
+        for (int i = 0; i < NX; ++i) bl.P[i][i] += reg_state;
+      }
+    }
+    const double rest = bl.phase2(J, j);
     jcst = jcst + rest;
     double* g = gains + (size_t)t * L::gain_stride * n_slots + s;
 #pragma unroll

@@ -15,6 +15,7 @@
 namespace ilqc {
 extern thread_local int g_sim_tid;
 typedef void* stream_t;
+inline long long& launch_counter() { static long long n = 0; return n; }
 }
 #define ILQC_GLOBAL static void
 #define ILQC_GLOBAL_LB(minblocks) static void
@@ -32,6 +33,8 @@ typedef void* stream_t;
 #include <cuda_runtime.h>
 namespace ilqc {
 typedef cudaStream_t stream_t;
+// number of kernels this library has launched (ilqc_launch_count; bench.py reports it as gpu_launches)
+inline long long& launch_counter() { static long long n = 0; return n; }
 }
 #define ILQC_GLOBAL __global__ void
 #define ILQC_GLOBAL_LB(minblocks) __global__ void __launch_bounds__(ILQC_BLOCK, minblocks)
@@ -39,7 +42,10 @@ typedef cudaStream_t stream_t;
 #define ILQC_UNPAREN(...) __VA_ARGS__
 #define ILQC_LAUNCH(kern, n, block, stream, ...)                                                   \
   do {                                                                                             \
-    if ((n) > 0) ILQC_UNPAREN kern<<<((n) + (block)-1) / (block), (block), 0, (stream)>>>(__VA_ARGS__); \
+    if ((n) > 0) {                                                                                 \
+      ILQC_UNPAREN kern<<<((n) + (block)-1) / (block), (block), 0, (stream)>>>(__VA_ARGS__);        \
+      ++::ilqc::launch_counter();                                                                  \
+    }                                                                                              \
   } while (0)
 #define ILQC_LAUNCH_OK() ((int)cudaGetLastError())
 #endif

@@ -57,14 +57,25 @@ struct Bell {
   double Q[NU][NU];  // upper triangle
   double q[NU];
   double R[NX][NU];
+  // intermediates carried from phase1 to phase2
+  double G[NU][NX];
+  double Hm[NU][NU];
+  double gq[NU];
+  double jt[NX];
   // results
   double K[NU][NX];
   double k[NU];
 
-  // J (packed upper, sym_idx) and j are updated in place; returns `rest`
-  ILQC_HD double step(double (&J)[NJ], double (&j)[NX]) {
+  // The step is split in two phases so that the state-cost operands (P, p) can be loaded AFTER everything
+  // that needs N, B and W has been consumed: the recursion sits at the 255-register limit and every value
+  // kept live across the whole step turns into local-memory traffic (ncu: half of the backward kernel's
+  // stall cycles were long_scoreboard on spills).  J is updated in place: J'(i,c) only reads J(i,c).
+  //
+  // phase1 needs N, B, Q, q (and R when Pat::QUAD):
+  //   W = J N ; JB = J B ; H = Q + B^T JB ; gq = q + B^T j ; G = R^T + JB^T + B^T W ; jt = j + N^T j ;
+  //   J += W + W^T + N^T W
+  ILQC_HD void phase1(double (&J)[NJ], const double (&j)[NX]) {
     auto Jat = [&](int a, int b) -> double { return J[sym_idx(a, b, NX)]; };
-    // W = J N (only the active columns of N)
     double W[NX][NX];
     static_for<NX>([&](auto C) {
       constexpr int c = C;
@@ -80,7 +91,6 @@ struct Bell {
         });
       }
     });
-    // JB = J B
     double JB[NX][NU];
     static_for<NU>([&](auto U) {
       constexpr int u = U;
@@ -94,26 +104,7 @@ struct Bell {
         JB[i][u] = acc;
       });
     });
-    // G = R^T + B^T (J + W)   (NU x NX)
-    double G[NU][NX];
-    static_for<NU>([&](auto U) {
-      constexpr int u = U;
-      static_for<NX>([&](auto C) {
-        constexpr int c = C;
-        double acc = JB[c][u];
-        if constexpr (Pat::QUAD && Pat::Rm(c, u)) acc += R[c][u];
-        if constexpr (Pat::Nm.col_any(c)) {
-          static_for<NX>([&](auto Rr) {
-            constexpr int r = Rr;
-            if constexpr (Pat::Bm(r, u)) acc += B[r][u] * W[r][c];
-          });
-        }
-        G[u][c] = acc;
-      });
-    });
-    // H = Q + B^T J B (symmetric: upper computed, mirrored) ; gq = q + B^T j
-    double Hm[NU][NU];
-    double gq[NU];
+    // H = Q + B^T J B (upper computed, mirrored) ; gq = q + B^T j
     static_for<NU>([&](auto U) {
       constexpr int u = U;
       static_for<NU>([&](auto V) {
@@ -139,8 +130,56 @@ struct Bell {
     for (int u = 0; u < NU; ++u)
 #pragma unroll
       for (int v = 0; v < u; ++v) Hm[u][v] = Hm[v][u];
+    // G = R^T + B^T (J + W)   (NU x NX);  B^T J = (J B)^T because J is symmetric
+    static_for<NU>([&](auto U) {
+      constexpr int u = U;
+      static_for<NX>([&](auto C) {
+        constexpr int c = C;
+        double acc = JB[c][u];
+        if constexpr (Pat::QUAD && Pat::Rm(c, u)) acc += R[c][u];
+        if constexpr (Pat::Nm.col_any(c)) {
+          static_for<NX>([&](auto Rr) {
+            constexpr int r = Rr;
+            if constexpr (Pat::Bm(r, u)) acc += B[r][u] * W[r][c];
+          });
+        }
+        G[u][c] = acc;
+      });
+    });
+    // jt = j + N^T j
+    static_for<NX>([&](auto I) {
+      constexpr int i = I;
+      double acc = j[i];
+      static_for<NX>([&](auto Rr) {
+        constexpr int r = Rr;
+        if constexpr (Pat::Nm(r, i)) acc += N[r][i] * j[r];
+      });
+      jt[i] = acc;
+    });
+    // J += W + W^T + N^T W  (upper triangle, in place)
+    static_for<NX>([&](auto I) {
+      constexpr int i = I;
+      static_for<NX>([&](auto C) {
+        constexpr int c = C;
+        if constexpr (c >= i && (Pat::Nm.col_any(c) || Pat::Nm.col_any(i))) {
+          double acc = J[sym_idx(i, c, NX)];
+          if constexpr (Pat::Nm.col_any(c)) acc += W[i][c];
+          if constexpr (Pat::Nm.col_any(i)) acc += W[c][i];
+          if constexpr (Pat::Nm.col_any(c) && Pat::Nm.col_any(i)) {
+            static_for<NX>([&](auto Rr) {
+              constexpr int r = Rr;
+              if constexpr (Pat::Nm(r, i)) acc += N[r][i] * W[r][c];
+            });
+          }
+          J[sym_idx(i, c, NX)] = acc;
+        }
+      });
+    });
+  }
 
-    // solve H [X | x] = [G | gq] by LU with partial pivoting ; K = -X, k = -x
+  // phase2 needs P, p:  K = -H^{-1} G ; k = -H^{-1} gq (LU with partial pivoting, both right-hand sides at
+  // once) ; J += P + G^T K ; j = jt + p + G^T k ; returns rest = gq.k / 2
+  ILQC_HD double phase2(double (&J)[NJ], double (&j)[NX]) {
     double rhs[NU][NX + 1];
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
@@ -195,55 +234,40 @@ struct Bell {
       for (int c = 0; c < NX; ++c) K[u][c] = -rhs[u][c];
       k[u] = -rhs[u][NX];
     }
-
-    // rest = (q + B^T j) . k / 2
     double rest = 0.0;
 #pragma unroll
     for (int u = 0; u < NU; ++u) rest += gq[u] * k[u];
     rest *= 0.5;
-
-    // j' = p + j + N^T j + G^T k
-    double jn[NX];
+    // j = jt + p + G^T k
     static_for<NX>([&](auto I) {
       constexpr int i = I;
-      double acc = j[i];
+      double acc = jt[i];
       if constexpr (Pat::pm(0, i)) acc += p[i];
-      static_for<NX>([&](auto Rr) {
-        constexpr int r = Rr;
-        if constexpr (Pat::Nm(r, i)) acc += N[r][i] * j[r];
-      });
 #pragma unroll
       for (int u = 0; u < NU; ++u) acc += G[u][i] * k[u];
-      jn[i] = acc;
+      j[i] = acc;
     });
-    // J' = P + J + W + W^T + N^T W + G^T K  (upper triangle)
-    double Jn[NJ];
+    // J += P + G^T K  (upper triangle, in place)
     static_for<NX>([&](auto I) {
       constexpr int i = I;
       static_for<NX>([&](auto C) {
         constexpr int c = C;
         if constexpr (c >= i) {
-          double acc = Jat(i, c);
+          double acc = J[sym_idx(i, c, NX)];
           if constexpr (Pat::Pm(i, c)) acc += P[i][c];
-          if constexpr (Pat::Nm.col_any(c)) acc += W[i][c];
-          if constexpr (Pat::Nm.col_any(i)) acc += W[c][i];
-          if constexpr (Pat::Nm.col_any(c) && Pat::Nm.col_any(i)) {
-            static_for<NX>([&](auto Rr) {
-              constexpr int r = Rr;
-              if constexpr (Pat::Nm(r, i)) acc += N[r][i] * W[r][c];
-            });
-          }
 #pragma unroll
           for (int u = 0; u < NU; ++u) acc += G[u][i] * K[u][c];
-          Jn[sym_idx(i, c, NX)] = acc;
+          J[sym_idx(i, c, NX)] = acc;
         }
       });
     });
-#pragma unroll
-    for (int i = 0; i < NJ; ++i) J[i] = Jn[i];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) j[i] = jn[i];
     return rest;
+  }
+
+  // whole step with all operands already loaded
+  ILQC_HD double step(double (&J)[NJ], double (&j)[NX]) {
+    phase1(J, j);
+    return phase2(J, j);
   }
 };
 

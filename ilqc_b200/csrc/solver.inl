@@ -453,10 +453,10 @@ inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 // Threads one wave of the register-heavy kernels keeps resident (256 per SM at 255 registers/thread).
 // Line-search rounds with fewer searching problems than this evaluate several candidates per problem at
 // once: the speculative candidates ride on SMs that would otherwise idle.
-// 640 threads per SM (= one full wave of the roll-out kernel at 100 registers, 2.5 waves of the backward
-// kernel) measured best on the bicycle workload: profiles/r01_tuning_scheduler.txt
+// 512 threads per SM = exactly one resident wave of the roll-out kernel (128 registers) and two of the
+// backward kernel; measured best on the bicycle workload (profiles/r01_tuning_scheduler.txt).
 #ifndef ILQC_WAVE_THREADS_PER_SM
-#define ILQC_WAVE_THREADS_PER_SM 640
+#define ILQC_WAVE_THREADS_PER_SM 512
 #endif
 inline int wave_slots() {
 #if defined(ILQC_HOSTSIM)

@@ -188,6 +188,9 @@ int ilqc_from_soa(const double* src, double* dst, int B, int n, void* stream);
 int ilqc_profile_enable(int enable);
 int ilqc_profile_read(double* ms, int64_t* launches, int64_t* units, int n);
 
+/* Number of kernels launched by this library since the last reset (all entry points, bookkeeping included). */
+long long ilqc_launch_count(int reset);
+
 /* FP64 DFMA micro-benchmark used for the roofline denominator: returns achieved FLOP/s (2 per DFMA). */
 int ilqc_fp64_peak(int iters, double* flops_per_s, void* stream);
 

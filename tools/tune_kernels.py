@@ -30,8 +30,9 @@ def main():
     B = 32768
     env, x0, w = make_batch(B, 1236)
     libs = {"default": _lib.CUDA_LIB_PATH}
-    for p in sorted(glob.glob(os.path.join(ROOT, "ilqc_b200", "build", "variants", "libilqc_*.so"))):
-        libs[os.path.basename(p)[8:-3]] = p
+    if not os.environ.get("ILQC_TUNE_DEFAULT_ONLY"):
+        for p in sorted(glob.glob(os.path.join(ROOT, "ilqc_b200", "build", "variants", "libilqc_*.so"))):
+            libs[os.path.basename(p)[8:-3]] = p
     print("variant, kernel, n_threads, ms, threads_per_ms")
     for tag, path in libs.items():
         eng = Engine(_lib.bind(path), torch.device("cuda", 0))
