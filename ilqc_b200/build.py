@@ -18,7 +18,8 @@ CSRC = os.path.join(PKG, "csrc")
 HOSTSIM = os.path.join(ROOT, "tests", "hostsim")
 CUDA_LIB = os.path.join(PKG, "libilqc_b200.so")
 HOSTSIM_LIB = os.path.join(HOSTSIM, "libilqc_hostsim.so")
-N_MODELS = 4
+# model translation units: public ids 0-3 + the three-control-set (`rk4`) variants 5-7 (csrc/models.cuh)
+MODEL_IDS = (0, 1, 2, 3, 5, 6, 7)
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -55,7 +56,7 @@ def build_cuda(verbose=True, force=False):
     obj_dir = os.path.join(PKG, "build")
     os.makedirs(obj_dir, exist_ok=True)
     jobs = []
-    for k in range(N_MODELS):
+    for k in MODEL_IDS:
         jobs.append((os.path.join(obj_dir, f"model_{k}.o"),
                      ["nvcc", *NVCC_FLAGS, f"-DILQC_MODEL_INST={k}", "-c", os.path.join(CSRC, "model_inst.cu")]))
     jobs.append((os.path.join(obj_dir, "dense.o"), ["nvcc", *NVCC_FLAGS, "-c", os.path.join(CSRC, "dense.cu")]))
@@ -84,7 +85,7 @@ def build_hostsim(verbose=True, force=False):
     os.makedirs(obj_dir, exist_ok=True)
     srcs = [os.path.join(HOSTSIM, f) for f in ("hostsim_api.cpp", "hostsim_model.cpp", "hostsim_dense.cpp")]
     jobs = []
-    for k in range(N_MODELS):
+    for k in MODEL_IDS:
         jobs.append((os.path.join(obj_dir, f"model_{k}.o"),
                      ["g++", *GXX_FLAGS, f"-DILQC_MODEL_INST={k}", "-c", srcs[1]]))
     jobs.append((os.path.join(obj_dir, "dense.o"), ["g++", *GXX_FLAGS, "-c", srcs[2]]))

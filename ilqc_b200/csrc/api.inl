@@ -62,7 +62,7 @@ int ilqc_rollout_cost(const ilqc_model_desc* m, int B, const double* x0, const d
   int rc = get_dims(m, &d);
   if (rc) return rc;
   if (B <= 0 || !x0 || !cmd) return ILQC_E_ARG;
-  ILQC_FOR_MODEL(m->model, return LM::forward(0, *m, B, B, nullptr, x0, cmd, nullptr, traj, cost_t, total, nullptr, (stream_t)stream));
+  ILQC_FOR_MODEL(effective_model(*m), return LM::forward(0, *m, B, B, nullptr, x0, cmd, nullptr, traj, cost_t, total, nullptr, (stream_t)stream));
   return 0;
 }
 
@@ -72,7 +72,7 @@ int ilqc_linearize(const ilqc_model_desc* m, int B, const double* x0, const doub
   int rc = get_dims(m, &d);
   if (rc) return rc;
   if (B <= 0 || !x0 || !cmd || !lin) return ILQC_E_ARG;
-  ILQC_FOR_MODEL(m->model, return LM::forward(1, *m, B, B, nullptr, x0, cmd, lin, traj, nullptr, total, nullptr, (stream_t)stream));
+  ILQC_FOR_MODEL(effective_model(*m), return LM::forward(1, *m, B, B, nullptr, x0, cmd, lin, traj, nullptr, total, nullptr, (stream_t)stream));
   return 0;
 }
 
@@ -84,7 +84,7 @@ int ilqc_expand_dense(const ilqc_model_desc* m, int B, const double* x0, const d
   if (rc) return rc;
   if (B <= 0 || !x0 || !cmd || !A || !Bm || !p || !P || !q || !Q) return ILQC_E_ARG;
   if (order >= 2 && (!lam || !Hxx || !Hxu || !Huu)) return ILQC_E_ARG;
-  ILQC_FOR_MODEL(m->model, return LM::expand_dense(*m, B, x0, cmd, order, A, Bm, p, P, q, Q, lam, Hxx, Hxu, Huu,
+  ILQC_FOR_MODEL(effective_model(*m), return LM::expand_dense(*m, B, x0, cmd, order, A, Bm, p, P, q, Q, lam, Hxx, Hxu, Huu,
                                                    (stream_t)stream));
   return 0;
 }
@@ -112,7 +112,7 @@ int ilqc_backward(const ilqc_model_desc* m, int mode, int B, int n_slots, const 
   if (rc) return rc;
   if (B <= 0 || n_slots <= 0 || !reg_ctrl || !lin || !gains || !jcst) return ILQC_E_ARG;
   if (mode != ILQC_BWD_LINQUAD && (!traj || !cmd)) return ILQC_E_ARG;
-  ILQC_FOR_MODEL(m->model, return LM::backward(mode, *m, B, n_slots, prob, nullptr, n_slots, reg_ctrl, reg_state, lin,
+  ILQC_FOR_MODEL(effective_model(*m), return LM::backward(mode, *m, B, n_slots, prob, nullptr, n_slots, reg_ctrl, reg_state, lin,
                                                traj, cmd, gains, jcst, feasible, (stream_t)stream));
   return 0;
 }
@@ -128,7 +128,7 @@ int ilqc_rollout(const ilqc_model_desc* m, int kind, int B, int n_slots, const i
   if (kind == ILQC_ROLL_EXACT && (!traj || !gains)) return ILQC_E_ARG;
   if (kind == ILQC_ROLL_LIN && (!lin || !gains)) return ILQC_E_ARG;
   if (kind == ILQC_ROLL_GD && !grad) return ILQC_E_ARG;
-  ILQC_FOR_MODEL(m->model, return LM::rollout(kind, *m, B, n_slots, prob, gslot, n_slots, nullptr, n_slots, step, x0, cmd,
+  ILQC_FOR_MODEL(effective_model(*m), return LM::rollout(kind, *m, B, n_slots, prob, gslot, n_slots, nullptr, n_slots, step, x0, cmd,
                                               traj, lin, gains, grad, diff, newval, diffsq, (stream_t)stream));
   return 0;
 }
@@ -140,7 +140,7 @@ int ilqc_grad_obj(const ilqc_model_desc* m, int B, const double* lin, double* gr
   if (rc) return rc;
   if (B <= 0 || !lin || !gnorm) return ILQC_E_ARG;
   (void)cnorm;
-  ILQC_FOR_MODEL(m->model, return LM::adjoint(*m, B, B, nullptr, lin, grad, gnorm, (stream_t)stream));
+  ILQC_FOR_MODEL(effective_model(*m), return LM::adjoint(*m, B, B, nullptr, lin, grad, gnorm, (stream_t)stream));
   return 0;
 }
 

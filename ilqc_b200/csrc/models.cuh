@@ -116,29 +116,31 @@ ILQC_HD int load_t0(const ilqc_model_desc& m, int b) { return m.pp_t0 ? ILQC_LDG
 // integrators (discretization.py).  f(const S* x, S* dx) evaluates the continuous dynamics with the
 // controls captured; N = number of integrated components.
 // ---------------------------------------------------------------------------------------------------
-template <class S, int N, class F>
-ILQC_HD void integrate_cst_ctrl(int integ, double dt, F&& f, const S (&x)[N], S (&xn)[N]) {
-  if (integ == ILQC_INT_EULER) {
+// VAR = runge_kutta4 with three control sets per step (discretization.py:22-39): set 0 for k1, set 1 for k2
+// and k3, set 2 for k4.  f(set, s, k) evaluates the continuous dynamics at stage state s with control set `set`.
+template <class S, int N, bool VAR, class F>
+ILQC_HD void integrate(int integ, double dt, F&& f, const S (&x)[N], S (&xn)[N]) {
+  if (!VAR && integ == ILQC_INT_EULER) {
     S k[N];
-    f(x, k);
+    f(0, x, k);
 #pragma unroll
     for (int i = 0; i < N; ++i) xn[i] = x[i] + dt * k[i];
   } else {
-    // runge_kutta4_cst_ctrl: state + dt*(k1 + 2*k2 + 2*k3 + k4)/6 with stage states state + dt*k1/2,
-    // state + dt*k2/2, state + dt*k3.  Written as a rolled loop over the four stages so that the (large,
-    // transcendental-heavy) dynamics body is instantiated once: 4x less code than the unrolled form, which
-    // matters for the instruction cache (ncu: 22 % of the expansion kernel's stall cycles were
-    // no_instruction).  Bit-identical to the unrolled formulas: x/2 == x*0.5 and 1*k, 2*k are exact.
-    // (measured on B200, profiles/r01_tuning_kernels.txt: rolled is 9-12 % faster for the plain roll-out and
-    // cuts the spills of the second-order jets by a third, but 5 % slower for the first-order expansion,
-    // which keeps the unrolled form)
-    constexpr int kStageUnroll = (is_jet<S>::value && sizeof(S) <= sizeof(double) * 16) ? 4 : 1;
+    // state + dt*(k1 + 2*k2 + 2*k3 + k4)/6 with stage states state + dt*k1/2, state + dt*k2/2, state + dt*k3.
+    // Written as a loop over the four stages so that the (large, transcendental-heavy) dynamics body can be
+    // instantiated once: 4x less code than the unrolled form.  Bit-identical to the unrolled formulas:
+    // x/2 == x*0.5 and 1*k, 2*k are exact.  Measured on B200 (profiles/r01_tuning_kernels.txt): rolled is
+    // 9-12 % faster for the plain roll-out and cuts the spills of the second-order jets by a third, but is 5 %
+    // slower for the first-order expansion, which keeps the unrolled form (as do the three-control-set
+    // integrators, whose per-stage control set must be a compile-time index).
+    constexpr int kStageUnroll = (VAR || (is_jet<S>::value && sizeof(S) <= sizeof(double) * 16)) ? 4 : 1;
     S k[N], s[N], acc[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) s[i] = x[i];
 #pragma unroll(kStageUnroll)
     for (int stage = 0; stage < 4; ++stage) {
-      f(s, k);
+      const int set = VAR ? (stage == 0 ? 0 : (stage == 3 ? 2 : 1)) : 0;
+      f(set, s, k);
       const double wgt = (stage == 1 || stage == 2) ? 2.0 : 1.0;  // k1 + 2 k2 + 2 k3 + k4
       const double half = (stage < 2) ? 0.5 : 1.0;                 // next stage state: dt*k/2, dt*k/2, dt*k
 #pragma unroll
@@ -210,6 +212,8 @@ ILQC_HD S spline_deriv(const Seg& s, int spline, int ch, const S& f) {
 // ===================================================================================================
 template <int MODEL>
 struct Model;
+// internal ids of the three-control-set (`rk4`) variants: public model id + ILQC_MODEL_VAR_OFFSET
+#define ILQC_MODEL_VAR_OFFSET 4
 
 // ---------------------------------------------------------------------------------------------------
 template <>
@@ -218,22 +222,23 @@ struct Model<ILQC_MODEL_PENDULUM> {
   static constexpr int sv(int i) { constexpr int t[NX] = {0, 1}; return t[i]; }
   static constexpr int uv(int i) { constexpr int t[NU] = {2}; return t[i]; }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1}; return t[i]; }
-  static constexpr bool Q_DIAG = true;
   static constexpr auto Nm = full_mask<NX, NX>();
   static constexpr auto Bm = full_mask<NX, NU>();
   static constexpr auto pm = full_mask<1, NX>();
   static constexpr auto Pm = upper_of(full_mask<NX, NX>());
+  static ILQC_HD double passive_N(const ilqc_model_desc&, int, int) { return 0.0; }
+  static ILQC_HD double passive_B(const ilqc_model_desc&, int, int) { return 0.0; }
 
   // dyn (pendulum.py:56-66) + euler
   template <class S>
   static ILQC_HD void step(const ilqc_model_desc& m, const S (&x)[NX], const S (&u)[NU], S (&xn)[NX]) {
     const double g = m.phys[0], mm = m.phys[1], l = m.phys[2], mu = m.phys[3];
     const double c_sin = -g / l, c_fr = mu / (mm * (l * l)), c_u = 1.0 / (mm * (l * l));
-    auto f = [&](const S* s, S* d) {
+    auto f = [&](int, const S* s, S* d) {
       d[0] = s[1];
       d[1] = c_sin * jsin(s[0] + M_PI) - c_fr * s[1] + c_u * u[0];
     };
-    integrate_cst_ctrl<S, NX>(m.integrator, m.dt, f, x, xn);
+    integrate<S, NX, false>(m.integrator, m.dt, f, x, xn);
   }
   // cost_state (pendulum.py:82-87): time_iter is the index of the state the cost is charged on
   template <class S>
@@ -250,17 +255,20 @@ struct Model<ILQC_MODEL_PENDULUM> {
 };
 
 // ---------------------------------------------------------------------------------------------------
-template <>
-struct Model<ILQC_MODEL_CARTPOLE> {
-  static constexpr int NX = 4, NU = 1, NV = 4, NVC = 3;
+// CartPendulum (pendulum.py:115-238).  VAR: discretization='rk4', one control per control set (nu = 3).
+template <bool VAR>
+struct CartPoleT {
+  static constexpr int NSET = VAR ? 3 : 1;
+  static constexpr int NX = 4, NU = NSET, NV = 3 + NSET, NVC = 3;
   static constexpr int sv(int i) { constexpr int t[NX] = {-1, 0, 1, 2}; return t[i]; }
-  static constexpr int uv(int i) { constexpr int t[NU] = {3}; return t[i]; }
+  static constexpr int uv(int i) { return 3 + i; }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1, -1, 2}; return t[i]; }
-  static constexpr bool Q_DIAG = true;
   static constexpr auto Nm = parse_mask<NX, NX>(".xxx/.xxx/.xxx/.xxx");
   static constexpr auto Bm = full_mask<NX, NU>();
   static constexpr auto pm = parse_mask<1, NX>("xx.x");
   static constexpr auto Pm = parse_mask<NX, NX>("x.../.x../..../...x");
+  static ILQC_HD double passive_N(const ilqc_model_desc&, int, int) { return 0.0; }
+  static ILQC_HD double passive_B(const ilqc_model_desc&, int, int) { return 0.0; }
 
   // dyn (pendulum.py:180-198), literal ordering: unpack (x, xdot, th, thdot) = s0..s3, return
   // (xdot, thdot, dxdot, dthdot)
@@ -270,19 +278,19 @@ struct Model<ILQC_MODEL_CARTPOLE> {
     const double a11 = M + mm, a22 = I + mm * (l * l), ml = mm * l;
     const double d0 = I * (M + mm) + mm * (l * l) * M, d1 = (mm * mm) * (l * l);
     const double mgl = -mm * g * l;
-    auto f = [&](const S* s, S* d) {
+    auto f = [&](int set, const S* s, S* d) {
       const S xdot = s[1], th = s[2], thdot = s[3];
       const S sth = jsin(th), cth = jcos(th);
       const S a12 = ml * cth;
       const S detA = d0 + d1 * jsq(sth);
-      const S b1 = (ml * jsq(thdot)) * sth - b * xdot + u[0];
+      const S b1 = (ml * jsq(thdot)) * sth - b * xdot + u[set];
       const S b2 = mgl * sth;
       d[0] = xdot;
       d[1] = thdot;
       d[2] = (a22 * b1 - a12 * b2) / detA;
       d[3] = (a11 * b2 - a12 * b1) / detA;
     };
-    integrate_cst_ctrl<S, NX>(m.integrator, m.dt, f, x, xn);
+    integrate<S, NX, VAR>(m.integrator, m.dt, f, x, xn);
   }
   // cost_state (pendulum.py:225-238)
   template <class S>
@@ -295,16 +303,24 @@ struct Model<ILQC_MODEL_CARTPOLE> {
     }
     return c;
   }
+  // reg_ctrl * ctrl.dot(ctrl) (pendulum.py:217-222)
   static ILQC_HD double ctrl_cost(const ilqc_model_desc& m, const double (&u)[NU], double (&q)[NU],
                                   double (&Qd)[NU]) {
-    q[0] = 2.0 * m.reg_ctrl * u[0];
-    Qd[0] = 2.0 * m.reg_ctrl;
-    return m.reg_ctrl * (u[0] * u[0]);
+    double dot = 0.0;
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      dot += u[i] * u[i];
+      q[i] = 2.0 * m.reg_ctrl * u[i];
+      Qd[i] = 2.0 * m.reg_ctrl;
+    }
+    return m.reg_ctrl * dot;
   }
 };
+template <> struct Model<ILQC_MODEL_CARTPOLE> : CartPoleT<false> {};
+template <> struct Model<ILQC_MODEL_CARTPOLE + ILQC_MODEL_VAR_OFFSET> : CartPoleT<true> {};
 
 // ---------------------------------------------------------------------------------------------------
-// Car: shared cost code (car.py:190-302).  XI/YI/TI/VI = indices of x, y, tref, vtref in the state.
+// Car: shared cost code (car.py:190-302).
 // ---------------------------------------------------------------------------------------------------
 template <class S, int NX>
 ILQC_HD S car_state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x)[NX], int time_iter) {
@@ -357,80 +373,108 @@ ILQC_HD S car_state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x
   return c + bar;
 }
 
+// reg_ctrl * ctrl.dot(ctrl), or the tuple form reg[0]*(acc^2 + delta^2) + reg[1]*atref^2 summed over the
+// control sets (car.py:235-251: ctrl[::3], ctrl[1::3], ctrl[2::3])
 template <int NU>
 ILQC_HD double car_ctrl_cost(const ilqc_model_desc& m, const double (&u)[NU], double (&q)[NU], double (&Qd)[NU]) {
-  if (m.reg_ctrl_is_tuple) {
-    // reg_ctrl[0]*(a^2+delta^2) + reg_ctrl[1]*atref^2 (car.py:235-241)
-    const double r0 = m.reg_ctrl, r1 = m.reg_ctrl_tref;
-    q[0] = 2.0 * r0 * u[0]; q[1] = 2.0 * r0 * u[1]; q[2] = 2.0 * r1 * u[2];
-    Qd[0] = 2.0 * r0; Qd[1] = 2.0 * r0; Qd[2] = 2.0 * r1;
-    return r0 * (u[0] * u[0] + u[1] * u[1]) + r1 * (u[2] * u[2]);
-  }
-  double dot = 0.0;
+  double c0 = 0.0, c1 = 0.0;
 #pragma unroll
   for (int i = 0; i < NU; ++i) {
-    dot += u[i] * u[i];
-    q[i] = 2.0 * m.reg_ctrl * u[i];
-    Qd[i] = 2.0 * m.reg_ctrl;
+    const bool is_tref = (i % 3 == 2);
+    const double r = (m.reg_ctrl_is_tuple && is_tref) ? m.reg_ctrl_tref : m.reg_ctrl;
+    if (m.reg_ctrl_is_tuple && is_tref) c1 += u[i] * u[i]; else c0 += u[i] * u[i];
+    q[i] = 2.0 * r * u[i];
+    Qd[i] = 2.0 * r;
   }
-  return m.reg_ctrl * dot;
+  return m.reg_ctrl_is_tuple ? (m.reg_ctrl * c0 + m.reg_ctrl_tref * c1) : m.reg_ctrl * c0;
 }
 
-// reference-time double integrator (tref, vtref ; atref), the same for both car models (car.py:143-146)
-ILQC_HD void car_tref_step(const ilqc_model_desc& m, double tref, double vtref, double atref, double* trefn,
-                           double* vtrefn) {
+// reference-time double integrator (tref, vtref ; atref per control set), the same for both car models
+// (car.py:143-146, :186-188)
+template <bool VAR>
+ILQC_HD void car_tref_step(const ilqc_model_desc& m, double tref, double vtref, const double (&atref)[VAR ? 3 : 1],
+                           double* trefn, double* vtrefn) {
   const double x[2] = {tref, vtref};
   double xn[2];
-  auto f = [&](const double* s, double* d) { d[0] = s[1]; d[1] = atref; };
-  integrate_cst_ctrl<double, 2>(m.integrator, m.dt, f, x, xn);
+  auto f = [&](int set, const double* s, double* d) { d[0] = s[1]; d[1] = atref[set]; };
+  integrate<double, 2, VAR>(m.integrator, m.dt, f, x, xn);
   *trefn = xn[0];
   *vtrefn = xn[1];
 }
-// its constant Jacobian: d tref'/d vtref = dt ; d tref'/d atref = dt^2/2 (rk4) or 0 (euler) ; d vtref'/d atref = dt
-ILQC_HD double car_tref_B(const ilqc_model_desc& m) { return m.integrator == ILQC_INT_EULER ? 0.0 : (m.dt * m.dt) / 2.0; }
+// its constant Jacobian wrt the control set `set`:
+//   constant control: d tref'/d atref = dt^2/2 (rk4) or 0 (euler), d vtref'/d atref = dt
+//   three sets:       d tref'/d atref_i = (dt^2/6, dt^2/3, 0),      d vtref'/d atref_i = dt/6 * (1, 4, 1)
+template <bool VAR>
+ILQC_HD double car_tref_B(const ilqc_model_desc& m, int row_is_vtref, int set) {
+  const double dt = m.dt;
+  if (!VAR) {
+    if (row_is_vtref) return dt;
+    return m.integrator == ILQC_INT_EULER ? 0.0 : (dt * dt) / 2.0;
+  }
+  if (row_is_vtref) return (dt / 6.0) * (set == 1 ? 4.0 : 1.0);
+  return set == 0 ? (dt * dt) / 6.0 : (set == 1 ? (dt * dt) / 3.0 : 0.0);
+}
+// B mask of a car model: vehicle rows x control (a, delta) of every set, (tref, vtref) rows x atref of every
+// set; ACC_ROW = a row that only the acceleration enters (simple car's v), -1 if none
+template <int NX, int NU, int NVEH, int ACC_ROW>
+constexpr Mask<NX, NU> car_B_mask() {
+  Mask<NX, NU> k;
+  for (int i = 0; i < NX; ++i)
+    for (int j = 0; j < NU; ++j) {
+      if (i < NVEH) k.m[i][j] = (j % 3 != 2) && (i != ACC_ROW || j % 3 == 0);
+      else k.m[i][j] = (j % 3 == 2);
+    }
+  return k;
+}
 
 // ---------------------------------------------------------------------------------------------------
-template <>
-struct Model<ILQC_MODEL_CAR_SIMPLE> {
-  // state (x, y, phi, v, tref, vtref), ctrl (a, delta, atref)
-  static constexpr int NX = 6, NU = 3, NV = 4, NVC = 4;
+template <bool VAR>
+struct CarSimpleT {
+  // state (x, y, phi, v, tref, vtref), ctrl (a, delta, atref) per control set
+  static constexpr int NSET = VAR ? 3 : 1;
+  static constexpr int NX = 6, NU = 3 * NSET, NV = 2 + 2 * NSET, NVC = 4;
   static constexpr int sv(int i) { constexpr int t[NX] = {-1, -1, 0, 1, -1, -1}; return t[i]; }
-  static constexpr int uv(int i) { constexpr int t[NU] = {2, 3, -1}; return t[i]; }
+  static constexpr int uv(int k) { return (k % 3 == 2) ? -1 : 2 + 2 * (k / 3) + (k % 3); }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1, -1, -1, 2, 3}; return t[i]; }
-  static constexpr bool Q_DIAG = true;
   static constexpr auto Nm = parse_mask<NX, NX>("..xx../..xx../...x../....../.....x/......");
-  static constexpr auto Bm = parse_mask<NX, NU>("xx./xx./xx./x../..x/..x");
+  static constexpr auto Bm = car_B_mask<NX, NU, 4, 3>();
   static constexpr auto pm = parse_mask<1, NX>("xx..xx");
   static constexpr auto Pm = parse_mask<NX, NX>("xx..x./.x..x./....../....../....x./.....x");
 
   template <class S>
   static ILQC_HD void step(const ilqc_model_desc& m, const S (&x)[NX], const S (&u)[NU], S (&xn)[NX]) {
-    const S delta = ((2.0 / M_PI) * jatan(u[1])) * m.constrain_angle;
-    const S tand = jtan(delta);
+    S tand[NSET];
+    double atref[NSET];
+#pragma unroll
+    for (int g = 0; g < NSET; ++g) {
+      const S delta = ((2.0 / M_PI) * jatan(u[3 * g + 1])) * m.constrain_angle;
+      tand[g] = jtan(delta);
+      atref[g] = val(u[3 * g + 2]);
+    }
     const double carlength = 1.5 * m.car_l;
     // vehicle part: (x, y, phi, v)
     const S xv[4] = {x[0], x[1], x[2], x[3]};
     S xvn[4];
-    auto f = [&](const S* s, S* d) {
+    auto f = [&](int set, const S* s, S* d) {
       const S sphi = jsin(s[2]), cphi = jcos(s[2]);
       d[0] = s[3] * cphi;
       d[1] = s[3] * sphi;
-      d[2] = (s[3] * tand) / carlength;
-      d[3] = u[0];
+      d[2] = (s[3] * tand[set]) / carlength;
+      d[3] = u[3 * set];
     };
-    integrate_cst_ctrl<S, 4>(m.integrator, m.dt, f, xv, xvn);
+    integrate<S, 4, VAR>(m.integrator, m.dt, f, xv, xvn);
 #pragma unroll
     for (int i = 0; i < 4; ++i) xn[i] = xvn[i];
     double tn, vn;
-    car_tref_step(m, val(x[4]), val(x[5]), val(u[2]), &tn, &vn);
+    car_tref_step<VAR>(m, val(x[4]), val(x[5]), atref, &tn, &vn);
     xn[4] = make_cst<S>(tn);
     xn[5] = make_cst<S>(vn);
   }
   // constant-coefficient part of (N, B) that the jets do not carry
   static ILQC_HD double passive_N(const ilqc_model_desc& m, int i, int j) { return (i == 4 && j == 5) ? m.dt : 0.0; }
   static ILQC_HD double passive_B(const ilqc_model_desc& m, int i, int k) {
-    if (k != 2) return 0.0;
-    return i == 4 ? car_tref_B(m) : (i == 5 ? m.dt : 0.0);
+    if (k % 3 != 2 || i < 4) return 0.0;
+    return car_tref_B<VAR>(m, i == 5, k / 3);
   }
   template <class S>
   static ILQC_HD S state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x)[NX], int time_iter) {
@@ -441,61 +485,70 @@ struct Model<ILQC_MODEL_CAR_SIMPLE> {
     return car_ctrl_cost<NU>(m, u, q, Qd);
   }
 };
+template <> struct Model<ILQC_MODEL_CAR_SIMPLE> : CarSimpleT<false> {};
+template <> struct Model<ILQC_MODEL_CAR_SIMPLE + ILQC_MODEL_VAR_OFFSET> : CarSimpleT<true> {};
 
 // ---------------------------------------------------------------------------------------------------
-template <>
-struct Model<ILQC_MODEL_CAR_BICYCLE> {
-  // state (x, y, phi, vx, vy, vphi, tref, vtref), ctrl (a, delta, atref)
-  static constexpr int NX = 8, NU = 3, NV = 6, NVC = 4;
+template <bool VAR>
+struct CarBicycleT {
+  // state (x, y, phi, vx, vy, vphi, tref, vtref), ctrl (a, delta, atref) per control set
+  static constexpr int NSET = VAR ? 3 : 1;
+  static constexpr int NX = 8, NU = 3 * NSET, NV = 4 + 2 * NSET, NVC = 4;
   static constexpr int sv(int i) { constexpr int t[NX] = {-1, -1, 0, 1, 2, 3, -1, -1}; return t[i]; }
-  static constexpr int uv(int i) { constexpr int t[NU] = {4, 5, -1}; return t[i]; }
+  static constexpr int uv(int k) { return (k % 3 == 2) ? -1 : 4 + 2 * (k / 3) + (k % 3); }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1, -1, -1, -1, -1, 2, 3}; return t[i]; }
-  static constexpr bool Q_DIAG = true;
   static constexpr auto Nm =
       parse_mask<NX, NX>("..xxxx../..xxxx../...xxx../...xxx../...xxx../...xxx../.......x/........");
-  static constexpr auto Bm = parse_mask<NX, NU>("xx./xx./xx./xx./xx./xx./..x/..x");
+  static constexpr auto Bm = car_B_mask<NX, NU, 6, -1>();
   static constexpr auto pm = parse_mask<1, NX>("xx....xx");
   static constexpr auto Pm =
       parse_mask<NX, NX>("xx....x./.x....x./......../......../......../......../......x./.......x");
 
   template <class S>
   static ILQC_HD void step(const ilqc_model_desc& m, const S (&x)[NX], const S (&u)[NU], S (&xn)[NX]) {
-    // control squashing is stage-independent under constant control: evaluate once
-    const S delta = ((2.0 / M_PI) * jatan(u[1])) * m.constrain_angle;
+    // control squashing does not depend on the stage state: evaluate once per control set
     const double gap = m.acc_hi - m.acc_lo;
-    const S a = gap * jsigmoid((4.0 * u[0]) / gap) + m.acc_lo;
-    const S sdel = jsin(delta), cdel = jcos(delta);
+    S delta[NSET], acc[NSET], sdel[NSET], cdel[NSET];
+    double atref[NSET];
+#pragma unroll
+    for (int g = 0; g < NSET; ++g) {
+      delta[g] = ((2.0 / M_PI) * jatan(u[3 * g + 1])) * m.constrain_angle;
+      acc[g] = gap * jsigmoid((4.0 * u[3 * g]) / gap) + m.acc_lo;
+      sdel[g] = jsin(delta[g]);
+      cdel[g] = jcos(delta[g]);
+      atref[g] = val(u[3 * g + 2]);
+    }
     const double Cm1 = m.Cm1, Cm2 = m.Cm2, Cr0 = m.Cr0, Cr2 = m.Cr2, Br = m.Br, Cr = m.Cr, Dr = m.Dr, Bf = m.Bf,
                  Cf = m.Cf, Df = m.Df, mass = m.m, Iz = m.Iz, lf = m.lf, lr = m.lr;
     const S xv[6] = {x[0], x[1], x[2], x[3], x[4], x[5]};
     S xvn[6];
-    auto f = [&](const S* s, S* d) {
+    auto f = [&](int set, const S* s, S* d) {
       const S phi = s[2], vx = s[3], vy = s[4], vphi = s[5];
-      const S alphaf = delta - jatan2(vphi * lf + vy, vx);
+      const S alphaf = delta[set] - jatan2(vphi * lf + vy, vx);
       const S alphar = jatan2(vphi * lr - vy, vx);
       const S Fry = Dr * jsin(Cr * jatan(Br * alphar));
       const S Ffy = Df * jsin(Cf * jatan(Bf * alphaf));
-      const S Frx = (Cm1 - Cm2 * vx) * a - Cr0 - Cr2 * jsq(vx);
+      const S Frx = (Cm1 - Cm2 * vx) * acc[set] - Cr0 - Cr2 * jsq(vx);
       const S sphi = jsin(phi), cphi = jcos(phi);
       d[0] = cphi * vx - sphi * vy;
       d[1] = sphi * vx + cphi * vy;
       d[2] = vphi;
-      d[3] = (Frx - Ffy * sdel + (mass * vy) * vphi) / mass;
-      d[4] = (Fry + Ffy * cdel - (mass * vx) * vphi) / mass;
-      d[5] = ((Ffy * lf) * cdel - Fry * lr) / Iz;
+      d[3] = (Frx - Ffy * sdel[set] + (mass * vy) * vphi) / mass;
+      d[4] = (Fry + Ffy * cdel[set] - (mass * vx) * vphi) / mass;
+      d[5] = ((Ffy * lf) * cdel[set] - Fry * lr) / Iz;
     };
-    integrate_cst_ctrl<S, 6>(m.integrator, m.dt, f, xv, xvn);
+    integrate<S, 6, VAR>(m.integrator, m.dt, f, xv, xvn);
 #pragma unroll
     for (int i = 0; i < 6; ++i) xn[i] = xvn[i];
     double tn, vn;
-    car_tref_step(m, val(x[6]), val(x[7]), val(u[2]), &tn, &vn);
+    car_tref_step<VAR>(m, val(x[6]), val(x[7]), atref, &tn, &vn);
     xn[6] = make_cst<S>(tn);
     xn[7] = make_cst<S>(vn);
   }
   static ILQC_HD double passive_N(const ilqc_model_desc& m, int i, int j) { return (i == 6 && j == 7) ? m.dt : 0.0; }
   static ILQC_HD double passive_B(const ilqc_model_desc& m, int i, int k) {
-    if (k != 2) return 0.0;
-    return i == 6 ? car_tref_B(m) : (i == 7 ? m.dt : 0.0);
+    if (k % 3 != 2 || i < 6) return 0.0;
+    return car_tref_B<VAR>(m, i == 7, k / 3);
   }
   template <class S>
   static ILQC_HD S state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x)[NX], int time_iter) {
@@ -506,16 +559,13 @@ struct Model<ILQC_MODEL_CAR_BICYCLE> {
     return car_ctrl_cost<NU>(m, u, q, Qd);
   }
 };
+template <> struct Model<ILQC_MODEL_CAR_BICYCLE> : CarBicycleT<false> {};
+template <> struct Model<ILQC_MODEL_CAR_BICYCLE + ILQC_MODEL_VAR_OFFSET> : CarBicycleT<true> {};
 
-// Pendulum / CartPendulum carry every dependence in their jets
 template <class M>
-ILQC_HD double passive_N_of(const ilqc_model_desc& m, int i, int j) {
-  if constexpr (M::NX >= 6) return M::passive_N(m, i, j); else return 0.0;
-}
+ILQC_HD double passive_N_of(const ilqc_model_desc& m, int i, int j) { return M::passive_N(m, i, j); }
 template <class M>
-ILQC_HD double passive_B_of(const ilqc_model_desc& m, int i, int k) {
-  if constexpr (M::NX >= 6) return M::passive_B(m, i, k); else return 0.0;
-}
+ILQC_HD double passive_B_of(const ilqc_model_desc& m, int i, int k) { return M::passive_B(m, i, k); }
 
 // ---------------------------------------------------------------------------------------------------
 // derived compile-time layout of the packed expansion of model M (doubles per time step per problem):

@@ -50,12 +50,22 @@ inline int dev_sync(stream_t st) { return (int)cudaStreamSynchronize(st); }
 #endif
 
 // ---- model dispatch -----------------------------------------------------------------------------------
+// effective model id: public model id, + ILQC_MODEL_VAR_OFFSET for the three-control-set `rk4` integrator
+#ifndef ILQC_MODEL_VAR_OFFSET
+#define ILQC_MODEL_VAR_OFFSET 4
+#endif
+inline int effective_model(const ilqc_model_desc& m) {
+  return m.model + (m.integrator == ILQC_INT_RK4 ? ILQC_MODEL_VAR_OFFSET : 0);
+}
 #define ILQC_FOR_MODEL(model_id, CALL)                                   \
   switch (model_id) {                                                    \
     case ILQC_MODEL_PENDULUM: { using LM = Launch<ILQC_MODEL_PENDULUM>; CALL; } break;       \
     case ILQC_MODEL_CARTPOLE: { using LM = Launch<ILQC_MODEL_CARTPOLE>; CALL; } break;       \
     case ILQC_MODEL_CAR_SIMPLE: { using LM = Launch<ILQC_MODEL_CAR_SIMPLE>; CALL; } break;   \
     case ILQC_MODEL_CAR_BICYCLE: { using LM = Launch<ILQC_MODEL_CAR_BICYCLE>; CALL; } break; \
+    case ILQC_MODEL_CARTPOLE + ILQC_MODEL_VAR_OFFSET: { using LM = Launch<ILQC_MODEL_CARTPOLE + ILQC_MODEL_VAR_OFFSET>; CALL; } break;       \
+    case ILQC_MODEL_CAR_SIMPLE + ILQC_MODEL_VAR_OFFSET: { using LM = Launch<ILQC_MODEL_CAR_SIMPLE + ILQC_MODEL_VAR_OFFSET>; CALL; } break;   \
+    case ILQC_MODEL_CAR_BICYCLE + ILQC_MODEL_VAR_OFFSET: { using LM = Launch<ILQC_MODEL_CAR_BICYCLE + ILQC_MODEL_VAR_OFFSET>; CALL; } break; \
     default: return ILQC_E_ARG;                                          \
   }
 
@@ -105,11 +115,12 @@ struct ProfScope {
 struct Dims { int nx, nu, lin_stride, gain_stride; };
 inline int get_dims(const ilqc_model_desc* m, Dims* d) {
   if (!m) return ILQC_E_ARG;
-  if (m->integrator == ILQC_INT_RK4) return ILQC_E_UNSUPPORTED;  // 3-controls-per-step RK4: SURVEY 8(f)-1, not built yet
+  if (m->integrator < ILQC_INT_EULER || m->integrator > ILQC_INT_RK4) return ILQC_E_ARG;
+  if (m->integrator == ILQC_INT_RK4 && m->model == ILQC_MODEL_PENDULUM) return ILQC_E_UNSUPPORTED;  // Pendulum is Euler only (pendulum.py:68-71)
   if (m->model >= ILQC_MODEL_CAR_SIMPLE && m->cost == ILQC_COST_CONTOURING && m->time_penalty == ILQC_TP_DREF_SQUARED)
     return ILQC_E_UNSUPPORTED;  // adds a (tref,vtref) cross term outside the stored pattern
   if (m->model >= ILQC_MODEL_CAR_SIMPLE && m->termination != ILQC_TERM_LOOP) return ILQC_E_UNSUPPORTED;
-  ILQC_FOR_MODEL(m->model, LM::dims(&d->nx, &d->nu, &d->lin_stride, &d->gain_stride));
+  ILQC_FOR_MODEL(effective_model(*m), LM::dims(&d->nx, &d->nu, &d->lin_stride, &d->gain_stride));
   return 0;
 }
 
@@ -544,9 +555,9 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
 
   // iteration 0: objective of the initial controls (same arithmetic as every candidate evaluation), its
   // expansion and the metrics row 0 (run_min_algo.py:65-76)
-  ILQC_PROF(PROF_FORWARD0, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(0, md, B, B, nullptr, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st))));
-  ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
-  if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
+  ILQC_PROF(PROF_FORWARD0, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(0, md, B, B, nullptr, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st))));
+  ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
+  if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
   ILQC_LAUNCH((status_kernel), B, 256, st, P, B, 0, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
               n_done);
 
@@ -570,7 +581,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
       int n_pass = n_active;
       for (int esc = 0; esc < 16 && n_pass > 0; ++esc) {
         // slot == problem for these gains: thread a serves problem plist[a] and writes slot plist[a]
-        ILQC_PROF(PROF_BACKWARD, n_pass, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::backward(bwd_mode, md, B, n_pass, plist, plist, B, w.reg_prob, 0.0, w.lin,
+        ILQC_PROF(PROF_BACKWARD, n_pass, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::backward(bwd_mode, md, B, n_pass, plist, plist, B, w.reg_prob, 0.0, w.lin,
                                                          w.traj, cmd, w.gains, w.dec_unit, w.feas_prob, st))));
         if (!quad) break;
         ILQC_LAUNCH((escalate_kernel), B, 256, st, B, status, w.feas_prob, w.reg_prob, w.flags);
@@ -581,7 +592,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
       if (a->algo_type == ILQC_ALGO_CLASSIC) {
         // diff_cmd = roll_out_lin(traj, gains) once (algos_steps.py:153), candidates scale it
         ILQC_LAUNCH((fill_kernel), B, 256, st, B, w.step_roll, 1.0);
-        ILQC_PROF(PROF_ROLLOUT, n_active, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(ILQC_ROLL_LIN, md, B, n_active, w.list, w.list, B, w.list, B,
+        ILQC_PROF(PROF_ROLLOUT, n_active, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::rollout(ILQC_ROLL_LIN, md, B, n_active, w.list, w.list, B, w.list, B,
                                                         w.step_roll, x0, cmd, w.traj, w.lin, w.gains, nullptr, w.dir,
                                                         w.newval, w.diffsq, st))));
       }
@@ -596,19 +607,19 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
       ILQC_LAUNCH((make_slots_kernel), n_active, 256, st, P, n_active, w.list, w.s_try, w.prob, w.gslot, w.step_true,
                   w.step_roll, w.reg);
       if (a->algo_type == ILQC_ALGO_GD) {
-        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(ILQC_ROLL_GD, md, B, n_slots, w.prob, nullptr, 0, nullptr, n_slots, w.step_roll, x0,
+        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::rollout(ILQC_ROLL_GD, md, B, n_slots, w.prob, nullptr, 0, nullptr, n_slots, w.step_roll, x0,
                                                         cmd, w.traj, w.lin, nullptr, w.dir, w.diff, w.newval, w.diffsq,
                                                         st))));
       } else if (regmode) {
-        ILQC_PROF(PROF_BACKWARD, n_slots, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::backward(bwd_mode, md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
+        ILQC_PROF(PROF_BACKWARD, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::backward(bwd_mode, md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
                                                          w.gains, w.jcst, w.feas_slot, st))));
         const int kind = a->algo_type == ILQC_ALGO_DDP ? ILQC_ROLL_EXACT : ILQC_ROLL_LIN;
-        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, nullptr, n_slots, nullptr, n_slots, w.step_roll, x0, cmd,
+        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, nullptr, n_slots, nullptr, n_slots, w.step_roll, x0, cmd,
                                                         w.traj, w.lin, w.gains, nullptr, w.diff, w.newval, w.diffsq,
                                                         st))));
       } else {
         const int kind = a->algo_type == ILQC_ALGO_DDP ? ILQC_ROLL_EXACT : ILQC_ROLL_GD;
-        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, w.gslot, B, nullptr, n_slots, w.step_roll, x0, cmd,
+        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, w.gslot, B, nullptr, n_slots, w.step_roll, x0, cmd,
                                                         w.traj, w.lin, w.gains, w.dir, w.diff, w.newval, w.diffsq, st))));
       }
       ILQC_LAUNCH((ls_select_kernel), n_active, 128, st, P, n_active, B, n_slots, w.list, w.step_true, w.newval, w.diffsq,
@@ -621,8 +632,8 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
     if (ls_trips) ILQC_CHECK(dev_d2d(ls_trips + (size_t)(it - 1) * B, w.trips, sizeof(int32_t) * B, st));
 
     // re-expand at the accepted controls (algos_steps.py:376-378) and collect the metrics of this iteration
-    ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
-    if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
+    ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
+    if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
     ILQC_LAUNCH((status_kernel), B, 256, st, P, B, it, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
                 n_done);
   }

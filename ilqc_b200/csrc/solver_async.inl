@@ -88,7 +88,7 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
   ILQC_LAUNCH((fill_kernel), n_rows, 256, st, n_rows, step_rep, (double)NAN);
   if (ls_trips && n_iter > 0) ILQC_LAUNCH((fill_i32_kernel), n_iter * B, 256, st, n_iter * B, ls_trips, (int32_t)0);
   // objective of the initial controls with the arithmetic of every candidate evaluation
-  ILQC_PROF(PROF_FORWARD0, B, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(0, md, B, B, nullptr, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st))));
+  ILQC_PROF(PROF_FORWARD0, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(0, md, B, B, nullptr, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st))));
 
   for (;;) {
     ILQC_LAUNCH((compact_eq_kernel), 1, 1024, st, B, w.phase, (int)PHASE_LS, w.list, w.count);
@@ -103,8 +103,8 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
 #endif
     // ---- stream B: re-expansion, gradient, metrics row and next line-search set-up of the LIN problems ----
     if (n_lin > 0) {
-      ILQC_PROF_ON(sb, PROF_LINEARIZE, n_lin, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::forward(1, md, B, n_lin, w.ident, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, sb))));
-      if (need_grad) ILQC_PROF_ON(sb, PROF_ADJOINT, n_lin, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::adjoint(md, B, n_lin, w.ident, w.lin, w.dir, w.gnorm, sb))));
+      ILQC_PROF_ON(sb, PROF_LINEARIZE, n_lin, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, n_lin, w.ident, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, sb))));
+      if (need_grad) ILQC_PROF_ON(sb, PROF_ADJOINT, n_lin, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, n_lin, w.ident, w.lin, w.dir, w.gnorm, sb))));
       ILQC_LAUNCH((status_async_kernel), n_lin, 256, sb, P, n_lin, w.ident, B, n_iter, w.curr_val, w.gnorm, w.cnorm, stepsize,
                   w.s_try, w.dec_unit, w.trips, status, A);
     }
@@ -114,13 +114,13 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
       const int n_slots = n_ls * P.L;
       ILQC_LAUNCH((make_slots_kernel), n_ls, 256, st, P, n_ls, w.list, w.s_try, w.prob, w.gslot, w.step_true, w.step_roll, w.reg);
       if (a->algo_type == ILQC_ALGO_GD) {
-        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(ILQC_ROLL_GD, md, B, n_slots, w.prob, nullptr, 0, nullptr, n_slots, w.step_roll, x0,
+        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::rollout(ILQC_ROLL_GD, md, B, n_slots, w.prob, nullptr, 0, nullptr, n_slots, w.step_roll, x0,
                                                         cmd, w.traj, w.lin, nullptr, w.dir, w.diff, w.newval, w.diffsq, st))));
       } else {
-        ILQC_PROF(PROF_BACKWARD, n_slots, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::backward(bwd_mode, md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
+        ILQC_PROF(PROF_BACKWARD, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::backward(bwd_mode, md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
                                                          w.gains, w.jcst, w.feas_slot, st))));
         const int kind = a->algo_type == ILQC_ALGO_DDP ? ILQC_ROLL_EXACT : ILQC_ROLL_LIN;
-        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(md.model, ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, nullptr, n_slots, nullptr, n_slots, w.step_roll, x0, cmd,
+        ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, nullptr, n_slots, nullptr, n_slots, w.step_roll, x0, cmd,
                                                         w.traj, w.lin, w.gains, nullptr, w.diff, w.newval, w.diffsq, st))));
       }
       ILQC_LAUNCH((ls_select_kernel), n_ls, 128, st, P, n_ls, B, n_slots, w.list, w.step_true, w.newval, w.diffsq, w.jcst,

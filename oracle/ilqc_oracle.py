@@ -101,7 +101,17 @@ def rk4_cst(dyn, x, u, dt):
     return x + dt * (k1 + 2 * k2 + 2 * k3 + k4) / 6
 
 
-INTEGRATORS = {"euler": euler, "rk4_cst_ctrl": rk4_cst, "rk4cst": rk4_cst}
+def rk4_var(dyn, x, u, dt):
+    """runge_kutta4 with three control sets per step (discretization.py:22-39)."""
+    n = int(u.shape[0] / 3)
+    k1 = dyn(x, u[:n])
+    k2 = dyn(x + dt * k1 / 2, u[n:2 * n])
+    k3 = dyn(x + dt * k2 / 2, u[n:2 * n])
+    k4 = dyn(x + dt * k3, u[2 * n:])
+    return x + dt * (k1 + 2 * k2 + 2 * k3 + k4) / 6
+
+
+INTEGRATORS = {"euler": euler, "rk4_cst_ctrl": rk4_cst, "rk4cst": rk4_cst, "rk4": rk4_var}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -144,7 +154,7 @@ class CartPendulum(Env):
                  discretization="euler", x_limits=None, seed=0):
         super().__init__()
         self.horizon, self.dt, self.discretization = horizon, dt, discretization
-        self.dim_ctrl, self.dim_state = 1, 4
+        self.dim_ctrl, self.dim_state = (3 if discretization == "rk4" else 1), 4
         self.init_state = torch.zeros(4)
         if seed != 0:
             torch.manual_seed(seed)
@@ -203,6 +213,8 @@ class Car(Env):
             self.init_state = T([0.0, 0.0, phi_ref, vinit, 0.0, 0.0, 0.0, vinit])
             self.dim_ctrl, self.dim_state = 3, 8
             self.dyn = self.bicycle_model
+        if discretization == "rk4":
+            self.dim_ctrl *= 3
         self.c = BICYCLE_CONSTANTS
         self.obstacle = self.track.evaluate(T(tr.length / 20)) + T([0.2, 0.0])
 
@@ -258,7 +270,7 @@ class Car(Env):
             x_ref, y_ref = self.track.evaluate(T(t * self.vref * self.dt))
             cs = (x - x_ref) ** 2 + (y - y_ref) ** 2
         if isinstance(self.reg_ctrl, tuple):
-            cc = self.reg_ctrl[0] * (u[0] ** 2 + u[1] ** 2) + self.reg_ctrl[1] * u[2] ** 2
+            cc = self.reg_ctrl[0] * ((u[::3] ** 2).sum() + (u[1::3] ** 2).sum()) + self.reg_ctrl[1] * (u[2::3] ** 2).sum()
         else:
             cc = self.reg_ctrl * u.dot(u)
         return cs, cc

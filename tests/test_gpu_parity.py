@@ -150,3 +150,7 @@ def test_solve_host_matches_device_path(cuda_engine):
     steph = torch.full((256,), 100.0, dtype=torch.float64).pin_memory()
     rh = cuda_engine.solve_host(env, "ddp_linquad_reg", 2, x0h, cmdh, steph, weights=w)
     assert torch.equal(rh.cost, r.cost.cpu()) and torch.equal(cmdh, r.cmd.cpu()) and torch.equal(steph, r.stepsize.cpu())
+
+
+def test_lq_synth_dense_riccati_vs_dense_newton(cuda_engine):
+    pc.check_lq_synth(cuda_engine)

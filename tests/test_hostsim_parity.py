@@ -35,3 +35,7 @@ def test_run_teacher_forced(sim_engine, name):
 @pytest.mark.parametrize("name", [n for n in RUNS if n not in CHAOTIC])
 def test_run_free(sim_engine, name):
     pc.check_run_free(sim_engine, name)
+
+
+def test_lq_synth_dense_riccati_vs_dense_newton(sim_engine):
+    pc.check_lq_synth(sim_engine)
