@@ -161,6 +161,22 @@ ILQC_HD void integrate(int integ, double dt, F&& f, const S (&x)[N], S (&xn)[N])
 struct Seg {
   const double* c;  // 24 coefficients of the segment: [spline][channel][a,b,c,d]
 };
+// smooth_relu with eps = 1e-6 (torch_utils.py:44-69): x for x > eps, 0 for x < -eps, a cubic blend in between
+// (the reference multiplies the branches by boolean masks; the inactive branch contributes an exact 0)
+template <class S>
+ILQC_HD S smooth_relu(const S& x) {
+  const double eps = 1e-6;
+  const double xv = val(x);
+  if (xv > eps) return x;
+  if (xv >= -eps) {
+    const double x1 = -eps, x2 = eps, y1 = 0.0, y2 = eps;
+    const double a = 0.0 * (x2 - x1) - (y2 - y1), b = -1.0 * (x2 - x1) + (y2 - y1);
+    const S tx = (x - x1) / (x2 - x1);
+    const S omt = 1.0 - tx;
+    return omt * y1 + tx * y2 + (tx * omt) * (omt * a + tx * b);
+  }
+  return make_cst<S>(0.0);
+}
 template <class S>
 ILQC_HD Seg spline_locate(const ilqc_model_desc& m, const S& t, S* frac) {
   double tv = val(t);
@@ -172,6 +188,11 @@ ILQC_HD Seg spline_locate(const ilqc_model_desc& m, const S& t, S* frac) {
     if (r != 0.0 && ((r < 0.0) != (L < 0.0))) r += L;
     set_val(tw, r);  // shifts the value, keeps the derivatives
     tv = r;
+  } else {
+    // 'repeat_end_point': t <- smooth_min(t, L) = -smooth_relu(-t + L) + L (torch_utils.py:72, torch_spline.py:345)
+    const double L = m.track_len;
+    tw = -smooth_relu<S>(-t + L) + L;
+    tv = val(tw);
   }
   // bucketize(t, knots) (right=False) - 1, clamped: the last knot strictly below t, i.e. the segment with
   // knots[idx] < t <= knots[idx+1] (t <= knots[0] -> 0, t > knots[n_seg] -> n_seg-1).  The knots are arc

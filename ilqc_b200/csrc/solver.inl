@@ -119,7 +119,6 @@ inline int get_dims(const ilqc_model_desc* m, Dims* d) {
   if (m->integrator == ILQC_INT_RK4 && m->model == ILQC_MODEL_PENDULUM) return ILQC_E_UNSUPPORTED;  // Pendulum is Euler only (pendulum.py:68-71)
   if (m->model >= ILQC_MODEL_CAR_SIMPLE && m->cost == ILQC_COST_CONTOURING && m->time_penalty == ILQC_TP_DREF_SQUARED)
     return ILQC_E_UNSUPPORTED;  // adds a (tref,vtref) cross term outside the stored pattern
-  if (m->model >= ILQC_MODEL_CAR_SIMPLE && m->termination != ILQC_TERM_LOOP) return ILQC_E_UNSUPPORTED;
   ILQC_FOR_MODEL(effective_model(*m), LM::dims(&d->nx, &d->nu, &d->lin_stride, &d->gain_stride));
   return 0;
 }

@@ -76,6 +76,10 @@ class Track:
     def _locate(self, t):
         if self.loop:
             t = np.remainder(t, self.length)
+        else:
+            # smooth_min(t, L) away from the 1e-6 blend zone around L (torch_utils.py:72); the host only
+            # evaluates the splines at t = 0 and L/20 (initial heading, obstacle)
+            t = -(self.length - t) + self.length if self.length - t > 1e-6 else self.length
         idx = int(np.clip(np.searchsorted(self.knots, t, side="left") - 1, 0, self.n_seg - 1))
         return t - self.knots[idx], idx
 

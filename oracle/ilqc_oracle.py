@@ -59,6 +59,20 @@ def jac_t(output, inp, create_graph=False):
 # ------------------------------------------------------------------------------------------------------
 # splines (torch_spline.py:341-375)
 # ------------------------------------------------------------------------------------------------------
+def smooth_relu(x, eps=1e-6):
+    """torch_utils.py:44-69: cubic blend between 0 and x on [-eps, eps], branches selected by boolean masks."""
+    x1, y1, x2, y2 = -eps, T(0.0), eps, eps
+    k1, k2 = T(0.0), T(1.0)
+    a = k1 * (x2 - x1) - (y2 - y1)
+    b = -k2 * (x2 - x1) + (y2 - y1)
+    tx = (x - x1) / (x2 - x1)
+    return (x > eps) * x + (x >= -eps) * (x <= eps) * ((1 - tx) * y1 + tx * y2 + tx * (1 - tx) * ((1 - tx) * a + tx * b))
+
+
+def smooth_min(x, a):
+    return -smooth_relu(-x + a) + a
+
+
 class Spline:
     def __init__(self, track, which):
         self.t = T(track.knots)
@@ -70,6 +84,8 @@ class Spline:
     def _locate(self, t):
         if self.loop:
             t = t % self.length
+        else:
+            t = smooth_min(t, self.length)  # 'repeat_end_point' (torch_spline.py:344-345)
         idx = torch.bucketize(t.detach(), self.t) - 1
         idx = idx.clamp(0, self.b.size(0) - 1)
         return t - self.t[idx], idx

@@ -103,6 +103,9 @@ ENV_CASES = {
     "bcar_exact_h20": dict(env="real_car", track="simple", cost="exact", discretization="rk4_cst_ctrl",
                            reg_bar=0.0, horizon=20, dt=0.02),
     "bcar_circle_h20": dict(env="real_car", track="circle", horizon=20),
+    # open tracks: handle_termination='repeat_end_point' -> smooth_min(t, L) (torch_spline.py:344-345)
+    "bcar_line_h20": dict(env="real_car", track="line", horizon=20),
+    "scar_bend_h20": dict(env="simple_car", track="bend", horizon=20, dt=0.04),
 }
 
 
@@ -192,9 +195,11 @@ def dump_forward(env, cmd, n_lam=2, seed=0):
     return out
 
 
-def gen_lin():
+def gen_lin(only=None):
     """Short-horizon expansions for every env/integrator/cost combination, generic states."""
     for name, cfg in ENV_CASES.items():
+        if only and name not in only:
+            continue
         cfg = dict(cfg)
         cfg["horizon"] = min(cfg["horizon"], 8)
         if name == "cart_h50":
@@ -211,6 +216,11 @@ def gen_lin():
             x0[-2] = 0.3                 # tref
             if cfg["env"] == "real_car":
                 x0[3] = 1.2              # vx > 0
+        if cfg.get("track") in ("line", "bend"):
+            # start just before the end of the open track so that tref crosses it (and the 1e-6 blend zone
+            # of smooth_min is left behind within the horizon)
+            from envs.tracks.tracks import get_track
+            x0[-2] = float(max(get_track(cfg["track"])[0]._t)) - 0.02
         if cfg["env"] == "cart_pendulum":
             x0[0] = 1.95                 # near the x_limits barrier so relu^3 is active on some steps
             cmd = cmd + 1.0
@@ -220,6 +230,8 @@ def gen_lin():
         out.update(cfg_to_arrays(cfg))
         save("lin_" + name, **out)
         print(name, "%.1fs" % (time.time() - t0), flush=True)
+    if only:
+        return
     # a car pushed outside the track so that both border barriers get exercised, and a window that
     # starts late (init_time_iter>0, exact cost depends on it, car.py:229)
     cfg = dict(ENV_CASES["bcar_h25"]); cfg["horizon"] = 6
@@ -485,6 +497,8 @@ if __name__ == "__main__":
             gen_tracks()
         elif gname == "lin":
             gen_lin()
+        elif gname.startswith("lin:"):
+            gen_lin(only=gname[4:].split(","))
         elif gname == "lq":
             gen_lq()
         elif gname == "runs":
