@@ -132,7 +132,7 @@ def test_empty_and_edge_inputs(cuda_engine):
     from ilqc_b200.envs import Pendulum, Car
     env = Pendulum(horizon=5)
     with pytest.raises(_lib.IlqcError):
-        cuda_engine.solve(Car(model="real", discretization="rk4"), "ddp_linquad_reg", 1)   # not built yet
+        cuda_engine.solve(Car(model="real", time_penalty="dref_squared"), "ddp_linquad_reg", 1)   # not built
     r = cuda_engine.solve(env, "ddp_linquad_reg", 0)       # zero iterations: metrics row 0 only
     assert r.cost.shape == (1, 1) and torch.isfinite(r.cost).all()
     r = cuda_engine.solve(Pendulum(horizon=1), "ddp_linquad_reg", 2)   # shortest horizon
