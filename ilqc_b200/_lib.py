@@ -78,6 +78,7 @@ PROTOTYPES = {
     "ilqc_profile_read": (C.c_int, [C.POINTER(_d), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
     "ilqc_launch_count": (C.c_longlong, [C.c_int]),
     "ilqc_fp64_peak": (C.c_int, [C.c_int, C.POINTER(_d), _p]),
+    "ilqc_fastmath_eval": (C.c_int, [C.c_int, C.c_int, _p, _p, _p, _p, _p]),
 }
 
 

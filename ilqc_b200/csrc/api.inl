@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/ilqc_b200.h.  Shared by the product library (api.cu, nvcc)
 // and the test-only host simulator (tests/hostsim/api_hostsim.cpp).
 #include "launch.cuh"
+#include "fastmath.cuh"
 #include "solver.inl"
 #include "solver_async.inl"
 
@@ -11,6 +12,28 @@ int dense_lq_backward(int nx, int nu, int H, int B, int L, const double* A, cons
 int dense_rollout_lin(int nx, int nu, int H, int B, int L, const double* A, const double* Bm, const double* K,
                       const double* k, const double* step, double* diff, stream_t st);
 }
+
+
+namespace ilqc {
+// self-test of the device math layer (fastmath.cuh): evaluates one of its functions elementwise
+ILQC_GLOBAL fastmath_eval_kernel(int fn, int n, const double* a, const double* b, double* o0, double* o1) {
+  const int i = ILQC_TID;
+  if (i >= n) return;
+  const double x[1] = {a[i]}, y[1] = {b ? b[i] : 0.0};
+  double r0[1] = {0.0}, r1[1] = {0.0};
+  switch (fn) {
+    case 0: fm::sincos<1>(x, r0, r1); break;
+    case 1: fm::atan2<1>(x, y, r0); break;   // atan2(a, b)
+    case 2: fm::atan<1>(x, r0); break;
+    case 3: r0[0] = fm::div(x[0], y[0]); break;
+    case 4: r0[0] = fm::rcp(x[0]); break;
+    case 5: fm::sqrt_rsqrt(x[0], &r0[0], &r1[0]); break;
+    default: break;
+  }
+  o0[i] = r0[0];
+  if (o1) o1[i] = r1[0];
+}
+}  // namespace ilqc
 
 using namespace ilqc;
 
@@ -171,6 +194,12 @@ int ilqc_profile_read(double* ms, int64_t* launches, int64_t* units, int n) {
     p.ms[i] = 0; p.launches[i] = 0; p.units[i] = 0;
   }
   return PROF_N;
+}
+
+int ilqc_fastmath_eval(int fn, int n, const double* a, const double* b, double* o0, double* o1, void* stream) {
+  if (fn < 0 || fn > 5 || n <= 0 || !a || !o0 || ((fn == 1 || fn == 3) && !b)) return ILQC_E_ARG;
+  ILQC_LAUNCH((fastmath_eval_kernel), n, 256, (stream_t)stream, fn, n, a, b, o0, o1);
+  return ILQC_LAUNCH_OK();
 }
 
 long long ilqc_launch_count(int reset) {

@@ -8,6 +8,7 @@
 // jets live in registers (thread-per-problem mapping).
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace ilqc {
 
@@ -250,5 +251,231 @@ template <int N, int O> ILQC_HD Jet<N, O> jcube(const Jet<N, O>& a) {
 template <int N, int O> ILQC_HD Jet<N, O> jmax0(const Jet<N, O>& a) {
   return (a.v > 0.0) ? a : make_cst<Jet<N, O>>(0.0);
 }
+
+// ======================================================================================================
+// Math context: the elementary functions the car models call, in two flavours.
+//   MathCtx<true>   branch-free L-lane implementations of fastmath.cuh, valid on a stated argument range;
+//                   `bad` accumulates "an argument was outside that range" and the caller then redoes the
+//                   block with
+//   MathCtx<false>  the CUDA math library / plain IEEE division (the arithmetic of every other model).
+// Both act on doubles and on jets (chain rules on top of the value functions).
+// ======================================================================================================
+#ifndef ILQC_FASTMATH
+#define ILQC_FASTMATH 1
+#endif
+#if defined(__CUDA_ARCH__) || !defined(__CUDACC__)
+#define ILQC_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define ILQC_UNLIKELY(x) (x)
+#endif
+
+template <bool FAST>
+struct MathCtx {
+  static constexpr bool kFast = FAST;
+  bool bad = false;
+
+  // ---- value level -----------------------------------------------------------------------------------
+  template <int L>
+  ILQC_HD void sincos_v(const double (&a)[L], double (&s)[L], double (&c)[L]) {
+    if constexpr (FAST) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) bad |= !(::fabs(a[l]) < fm::kSinCosMaxArg);
+      fm::sincos<L>(a, s, c);
+    } else {
+#pragma unroll
+      for (int l = 0; l < L; ++l) { s[l] = ::sin(a[l]); c[l] = ::cos(a[l]); }
+    }
+  }
+  template <int L>
+  ILQC_HD void atan2_v(const double (&y)[L], const double (&x)[L], double (&o)[L]) {
+    if constexpr (FAST) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) bad |= fm::exp_out_of_range(::fabs(x[l]) + ::fabs(y[l]));
+      fm::atan2<L>(y, x, o);
+    } else {
+#pragma unroll
+      for (int l = 0; l < L; ++l) o[l] = ::atan2(y[l], x[l]);
+    }
+  }
+  template <int L>
+  ILQC_HD void atan_v(const double (&a)[L], double (&o)[L]) {
+    if constexpr (FAST) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) bad |= fm::too_big(a[l]);
+      fm::atan<L>(a, o);
+    } else {
+#pragma unroll
+      for (int l = 0; l < L; ++l) o[l] = ::atan(a[l]);
+    }
+  }
+  ILQC_HD double rcp_v(double b) {
+    if constexpr (FAST) {
+      bad |= fm::exp_out_of_range(b);
+      return fm::rcp(b);
+    } else {
+      return 1.0 / b;
+    }
+  }
+  // q = a/b and ib = 1/b with one reciprocal
+  ILQC_HD void divrcp_v(double a, double b, double* q, double* ib) {
+    if constexpr (FAST) {
+      bad |= fm::exp_out_of_range(b) | fm::too_big(a);
+      const double r = fm::rcp_raw(b);
+      *q = fm::div_with_rcp(a, b, r);
+      *ib = fm::div_with_rcp(1.0, b, r);
+    } else {
+      *q = a / b;
+      *ib = 1.0 / b;
+    }
+  }
+  ILQC_HD double div_v(double a, double b) {
+    if constexpr (FAST) {
+      bad |= fm::exp_out_of_range(b) | fm::too_big(a);
+      return fm::div(a, b);
+    } else {
+      return a / b;
+    }
+  }
+  // a / b for a loop-invariant b in the safe exponent window with rb = 1/b precomputed (3 FMA-class
+  // instructions, correctly rounded for finite a)
+  ILQC_HD double divc_v(double a, double b, double rb) {
+    if constexpr (FAST) return fm::div_with_rcp(a, b, rb);
+    else return a / b;
+  }
+
+  // ---- generic in S (double or Jet) ------------------------------------------------------------------------
+  template <class S, int L>
+  ILQC_HD void sincos(const S (&a)[L], S (&s)[L], S (&c)[L]) {
+    double av[L], sv[L], cv[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) av[l] = val(a[l]);
+    sincos_v<L>(av, sv, cv);
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      if constexpr (is_jet<S>::value) {
+        s[l] = chain1(a[l], sv[l], cv[l], -sv[l]);
+        c[l] = chain1(a[l], cv[l], -sv[l], -cv[l]);
+      } else {
+        s[l] = sv[l];
+        c[l] = cv[l];
+      }
+    }
+  }
+  template <class S, int L>
+  ILQC_HD void atan2(const S (&y)[L], const S (&x)[L], S (&o)[L]) {
+    double yv[L], xv[L], ov[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) { yv[l] = val(y[l]); xv[l] = val(x[l]); }
+    atan2_v<L>(yv, xv, ov);
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      if constexpr (is_jet<S>::value) {
+        const double ir2 = rcp_v(xv[l] * xv[l] + yv[l] * yv[l]);
+        const double fy = xv[l] * ir2, fx = -yv[l] * ir2;
+        const double fyy = -2.0 * xv[l] * yv[l] * ir2 * ir2;
+        const double fxy = (yv[l] * yv[l] - xv[l] * xv[l]) * ir2 * ir2;
+        o[l] = chain2(y[l], x[l], ov[l], fy, fx, fyy, fxy, -fyy);
+      } else {
+        o[l] = ov[l];
+      }
+    }
+  }
+  template <class S, int L>
+  ILQC_HD void atan(const S (&a)[L], S (&o)[L]) {
+    double av[L], ov[L];
+#pragma unroll
+    for (int l = 0; l < L; ++l) av[l] = val(a[l]);
+    atan_v<L>(av, ov);
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      if constexpr (is_jet<S>::value) {
+        const double d = rcp_v(1.0 + av[l] * av[l]);
+        o[l] = chain1(a[l], ov[l], d, -2.0 * av[l] * d * d);
+      } else {
+        o[l] = ov[l];
+      }
+    }
+  }
+  template <class S>
+  ILQC_HD S div(const S& a, const S& b) {
+    if constexpr (is_jet<S>::value) {
+      double q, ib;
+      divrcp_v(a.v, b.v, &q, &ib);
+      return chain2(a, b, q, ib, -q * ib, 0.0, -ib * ib, 2.0 * q * ib * ib);
+    } else {
+      return div_v(a, b);
+    }
+  }
+  template <class S>
+  ILQC_HD S div_cst_by(double a, const S& b) {
+    if constexpr (is_jet<S>::value) {
+      double q, ib;
+      divrcp_v(a, b.v, &q, &ib);
+      return chain1(b, q, -q * ib, 2.0 * q * ib * ib);
+    } else {
+      return div_v(a, b);
+    }
+  }
+  template <class S>
+  ILQC_HD S divc(const S& a, double b, double rb) {
+    if constexpr (is_jet<S>::value) {
+      S r;
+      r.v = divc_v(a.v, b, rb);
+#pragma unroll
+      for (int i = 0; i < S::NV; ++i) r.g[i] = a.g[i] * rb;
+#pragma unroll
+      for (int i = 0; i < S::NH; ++i) r.h[i] = a.h[i] * rb;
+      return r;
+    } else {
+      return divc_v(a, b, rb);
+    }
+  }
+  // torch.sigmoid: 1 / (1 + exp(-a))
+  template <class S>
+  ILQC_HD S sigmoid(const S& a) {
+    const double s = rcp_v(1.0 + ::exp(-val(a)));
+    if constexpr (is_jet<S>::value) {
+      const double d = s * (1.0 - s);
+      return chain1(a, s, d, d * (1.0 - 2.0 * s));
+    } else {
+      return s;
+    }
+  }
+  // v = sqrt(w) and iv = 1/sqrt(w)
+  template <class S>
+  ILQC_HD void sqrt_inv(const S& w, S* v, S* iv) {
+    double s, is;
+    if constexpr (FAST) {
+      bad |= fm::exp_out_of_range(val(w)) | (val(w) < 0.0);
+      fm::sqrt_rsqrt(val(w), &s, &is);
+    } else {
+      s = ::sqrt(val(w));
+      is = 1.0 / s;
+    }
+    if constexpr (is_jet<S>::value) {
+      const double is2 = is * is;
+      *v = chain1(w, s, 0.5 * is, (-0.25 * is) * is2);
+      *iv = chain1(w, is, (-0.5 * is) * is2, ((0.75 * is) * is2) * is2);
+    } else {
+      *v = s;
+      *iv = is;
+    }
+  }
+  template <class S>
+  ILQC_HD S log(const S& a) {
+    if constexpr (is_jet<S>::value) {
+      const double i = rcp_v(a.v);
+      return chain1(a, ::log(a.v), i, -i * i);
+    } else {
+      return ::log(a);
+    }
+  }
+};
+#if ILQC_FASTMATH
+using MathHot = MathCtx<true>;
+#else
+using MathHot = MathCtx<false>;
+#endif
+using MathExact = MathCtx<false>;
 
 }  // namespace ilqc

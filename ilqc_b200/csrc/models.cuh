@@ -149,8 +149,9 @@ ILQC_HD void integrate(int integ, double dt, F&& f, const S (&x)[N], S (&xn)[N])
         s[i] = x[i] + (dt * k[i]) * half;
       }
     }
+    MathHot mh;  // (dt * acc) / 6: quotient by a constant, correctly rounded in 3 FMAs (fastmath.cuh)
 #pragma unroll
-    for (int i = 0; i < N; ++i) xn[i] = x[i] + (dt * acc[i]) / 6.0;
+    for (int i = 0; i < N; ++i) xn[i] = x[i] + mh.divc(dt * acc[i], 6.0, 1.0 / 6.0);
   }
 }
 
@@ -343,26 +344,29 @@ template <> struct Model<ILQC_MODEL_CARTPOLE + ILQC_MODEL_VAR_OFFSET> : CartPole
 // ---------------------------------------------------------------------------------------------------
 // Car: shared cost code (car.py:190-302).
 // ---------------------------------------------------------------------------------------------------
-template <class S, int NX>
-ILQC_HD S car_state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x)[NX], int time_iter) {
+template <class S, int NX, class MX>
+ILQC_HD S car_state_cost_mx(MX& mx, const ilqc_model_desc& m, const Weights& w, const S (&x)[NX]) {
   const S& px = x[0];
   const S& py = x[1];
-  if (m.cost == ILQC_COST_EXACT) {
-    // time = time_iter * vref * dt is a constant of the graph (car.py:229-231)
-    const double time = ((double)time_iter * m.vref) * m.dt;
-    double fr;
-    const Seg sg = spline_locate<double>(m, time, &fr);
-    const double xr = spline_eval<double>(sg, 0, 0, fr), yr = spline_eval<double>(sg, 0, 1, fr);
-    return jsq(px - xr) + jsq(py - yr);
-  }
   const S& tref = x[NX - 2];
   const S& vtref = x[NX - 1];
   S fr;
   const Seg sg = spline_locate<S>(m, tref, &fr);
   const S xr = spline_eval<S>(sg, 0, 0, fr), yr = spline_eval<S>(sg, 0, 1, fr);
   const S dxr = spline_deriv<S>(sg, 0, 0, fr), dyr = spline_deriv<S>(sg, 0, 1, fr);
-  const S phi_ref = jatan2(dyr, dxr);
-  const S sp = jsin(phi_ref), cp = jcos(phi_ref);
+  S sp, cp;
+  if constexpr (MX::kFast) {
+    // sin / cos of phi_ref = atan2(dy, dx) are dy / |d| and dx / |d|: one reciprocal square root instead of
+    // atan2 + sin + cos (equal to the reference's composition up to rounding)
+    S nrm, inrm;
+    mx.sqrt_inv(jsq(dxr) + jsq(dyr), &nrm, &inrm);
+    sp = dyr * inrm;
+    cp = dxr * inrm;
+  } else {
+    const S phi_ref = jatan2(dyr, dxr);
+    sp = jsin(phi_ref);
+    cp = jcos(phi_ref);
+  }
   const S ex = px - xr, ey = py - yr;
   const S cont_err = sp * ex - cp * ey;
   const S lag_err = -cp * ex - sp * ey;
@@ -372,16 +376,25 @@ ILQC_HD S car_state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x
   else if (m.time_penalty == ILQC_TP_DREF) c = c - (w.reg_speed * vtref) * m.dt;
   else c = c - ((w.reg_speed * vtref) * m.dt) * tref;
   // barrier (car.py:255-302)
-  S bar = -1e-6 * jlog(vtref);
+  S bar = -1e-6 * mx.log(vtref);
   const double carwidth = 1.5 * m.car_w;
   const double pxv = val(px), pyv = val(py);  // point = torch.tensor([x, y]) is detached (car.py:262)
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const S bx = spline_eval<S>(sg, 1 + i, 0, fr), by = spline_eval<S>(sg, 1 + i, 1, fr);
     const S dbx = spline_deriv<S>(sg, 1 + i, 0, fr), dby = spline_deriv<S>(sg, 1 + i, 1, fr);
-    const S v = jsqrt(jsq(dbx) + jsq(dby));
     // normal = torch.tensor([dpos[1], -dpos[0]]) / v : numerator detached (car.py:267)
-    const S n0 = val(dby) / v, n1 = (-val(dbx)) / v;
+    S n0, n1;
+    if constexpr (MX::kFast) {
+      S v, iv;
+      mx.sqrt_inv(jsq(dbx) + jsq(dby), &v, &iv);
+      n0 = val(dby) * iv;
+      n1 = (-val(dbx)) * iv;
+    } else {
+      const S v = jsqrt(jsq(dbx) + jsq(dby));
+      n0 = val(dby) / v;
+      n1 = (-val(dbx)) / v;
+    }
     const S dot = (pxv - bx) * n0 + (pyv - by) * n1;
     if (i == 0) bar = bar + m.reg_bar * jcube(jmax0(carwidth / 2.0 - dot));
     else bar = bar + m.reg_bar * jcube(jmax0(dot + carwidth / 2.0));
@@ -392,6 +405,26 @@ ILQC_HD S car_state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x
     bar = bar + m.reg_obs * ((o * o) * o);
   }
   return c + bar;
+}
+template <class S, int NX>
+ILQC_HD S car_state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x)[NX], int time_iter) {
+  if (m.cost == ILQC_COST_EXACT) {
+    // time = time_iter * vref * dt is a constant of the graph (car.py:229-231)
+    const double time = ((double)time_iter * m.vref) * m.dt;
+    double fr;
+    const Seg sg = spline_locate<double>(m, time, &fr);
+    const double xr = spline_eval<double>(sg, 0, 0, fr), yr = spline_eval<double>(sg, 0, 1, fr);
+    return jsq(x[0] - xr) + jsq(x[1] - yr);
+  }
+  MathHot mx;
+  S c = car_state_cost_mx<S, NX>(mx, m, w, x);
+  if constexpr (MathHot::kFast) {
+    if (ILQC_UNLIKELY(mx.bad)) {  // an argument outside the fast functions' range: CUDA math library
+      MathExact me;
+      c = car_state_cost_mx<S, NX>(me, m, w, x);
+    }
+  }
+  return c;
 }
 
 // reg_ctrl * ctrl.dot(ctrl), or the tuple form reg[0]*(acc^2 + delta^2) + reg[1]*atref^2 summed over the
@@ -462,26 +495,64 @@ struct CarSimpleT {
   static constexpr auto pm = parse_mask<1, NX>("xx..xx");
   static constexpr auto Pm = parse_mask<NX, NX>("xx..x./.x..x./....../....../....x./.....x");
 
+  // steering: delta = 2/pi atan(u) * constrain_angle ; tan(delta) = sin / cos
+  template <class S, class MX>
+  static ILQC_HD void controls(MX& mx, const ilqc_model_desc& m, const S (&u)[NU], S (&tand)[NSET]) {
+    S ud[NSET], at[NSET];
+#pragma unroll
+    for (int g = 0; g < NSET; ++g) ud[g] = u[3 * g + 1];
+    if constexpr (MX::kFast) {
+      mx.atan(ud, at);
+      S delta[NSET], sd[NSET], cd[NSET];
+#pragma unroll
+      for (int g = 0; g < NSET; ++g) delta[g] = ((2.0 / M_PI) * at[g]) * m.constrain_angle;
+      mx.sincos(delta, sd, cd);
+#pragma unroll
+      for (int g = 0; g < NSET; ++g) tand[g] = mx.div(sd[g], cd[g]);
+    } else {
+#pragma unroll
+      for (int g = 0; g < NSET; ++g) tand[g] = jtan(((2.0 / M_PI) * jatan(ud[g])) * m.constrain_angle);
+    }
+  }
+  template <class S, class MX>
+  static ILQC_HD void dyn(MX& mx, double carlength, double rcarlength, const S& tand, const S& acc, const S* s, S* d) {
+    const S ph[1] = {s[2]};
+    S sphi[1], cphi[1];
+    mx.sincos(ph, sphi, cphi);
+    d[0] = s[3] * cphi[0];
+    d[1] = s[3] * sphi[0];
+    d[2] = mx.divc(s[3] * tand, carlength, rcarlength);
+    d[3] = acc;
+  }
   template <class S>
   static ILQC_HD void step(const ilqc_model_desc& m, const S (&x)[NX], const S (&u)[NU], S (&xn)[NX]) {
     S tand[NSET];
     double atref[NSET];
 #pragma unroll
-    for (int g = 0; g < NSET; ++g) {
-      const S delta = ((2.0 / M_PI) * jatan(u[3 * g + 1])) * m.constrain_angle;
-      tand[g] = jtan(delta);
-      atref[g] = val(u[3 * g + 2]);
+    for (int g = 0; g < NSET; ++g) atref[g] = val(u[3 * g + 2]);
+    {
+      MathHot mx;
+      controls<S>(mx, m, u, tand);
+      if constexpr (MathHot::kFast) {
+        if (ILQC_UNLIKELY(mx.bad)) {
+          MathExact me;
+          controls<S>(me, m, u, tand);
+        }
+      }
     }
-    const double carlength = 1.5 * m.car_l;
+    const double carlength = 1.5 * m.car_l, rcarlength = 1.0 / carlength;
     // vehicle part: (x, y, phi, v)
     const S xv[4] = {x[0], x[1], x[2], x[3]};
     S xvn[4];
     auto f = [&](int set, const S* s, S* d) {
-      const S sphi = jsin(s[2]), cphi = jcos(s[2]);
-      d[0] = s[3] * cphi;
-      d[1] = s[3] * sphi;
-      d[2] = (s[3] * tand[set]) / carlength;
-      d[3] = u[3 * set];
+      MathHot mx;
+      dyn<S>(mx, carlength, rcarlength, tand[set], u[3 * set], s, d);
+      if constexpr (MathHot::kFast) {
+        if (ILQC_UNLIKELY(mx.bad)) {
+          MathExact me;
+          dyn<S>(me, carlength, rcarlength, tand[set], u[3 * set], s, d);
+        }
+      }
     };
     integrate<S, 4, VAR>(m.integrator, m.dt, f, xv, xvn);
 #pragma unroll
@@ -525,38 +596,81 @@ struct CarBicycleT {
   static constexpr auto Pm =
       parse_mask<NX, NX>("xx....x./.x....x./......../......../......../......../......x./.......x");
 
+  // control squashing (car.py:150-158): does not depend on the stage state, evaluated once per control set
+  template <class S, class MX>
+  static ILQC_HD void controls(MX& mx, const ilqc_model_desc& m, const S (&u)[NU], S (&delta)[NSET], S (&acc)[NSET],
+                               S (&sdel)[NSET], S (&cdel)[NSET]) {
+    const double gap = m.acc_hi - m.acc_lo, rgap = 1.0 / gap;
+    S ud[NSET], at[NSET];
+#pragma unroll
+    for (int g = 0; g < NSET; ++g) ud[g] = u[3 * g + 1];
+    mx.atan(ud, at);
+#pragma unroll
+    for (int g = 0; g < NSET; ++g) {
+      delta[g] = ((2.0 / M_PI) * at[g]) * m.constrain_angle;
+      acc[g] = gap * mx.sigmoid(mx.divc(4.0 * u[3 * g], gap, rgap)) + m.acc_lo;
+    }
+    mx.sincos(delta, sdel, cdel);
+  }
+  struct Par {
+    double Cm1, Cm2, Cr0, Cr2, Br, Cr, Dr, Bf, Cf, Df, mass, Iz, lf, lr, rmass, rIz;
+  };
+  // bicycle_model (car.py:160-188) at one stage state; the front / rear tyre chains (atan2 -> atan -> sin) run
+  // as two lanes of the L-lane functions
+  template <class S, class MX>
+  static ILQC_HD void dyn(MX& mx, const Par& p, const S& delta, const S& acc, const S& sdel, const S& cdel,
+                          const S* s, S* d) {
+    const S phi = s[2], vx = s[3], vy = s[4], vphi = s[5];
+    const S ys[2] = {vphi * p.lf + vy, vphi * p.lr - vy}, xs[2] = {vx, vx};
+    S al[2];
+    mx.atan2(ys, xs, al);
+    const S alphaf = delta - al[0];
+    const S alphar = al[1];
+    const S ba[2] = {p.Br * alphar, p.Bf * alphaf};
+    S at[2];
+    mx.atan(ba, at);
+    const S sa[3] = {p.Cr * at[0], p.Cf * at[1], phi};
+    S sn[3], cs[3];
+    mx.sincos(sa, sn, cs);
+    const S Fry = p.Dr * sn[0];
+    const S Ffy = p.Df * sn[1];
+    const S Frx = (p.Cm1 - p.Cm2 * vx) * acc - p.Cr0 - p.Cr2 * jsq(vx);
+    const S sphi = sn[2], cphi = cs[2];
+    d[0] = cphi * vx - sphi * vy;
+    d[1] = sphi * vx + cphi * vy;
+    d[2] = vphi;
+    d[3] = mx.divc(Frx - Ffy * sdel + (p.mass * vy) * vphi, p.mass, p.rmass);
+    d[4] = mx.divc(Fry + Ffy * cdel - (p.mass * vx) * vphi, p.mass, p.rmass);
+    d[5] = mx.divc((Ffy * p.lf) * cdel - Fry * p.lr, p.Iz, p.rIz);
+  }
   template <class S>
   static ILQC_HD void step(const ilqc_model_desc& m, const S (&x)[NX], const S (&u)[NU], S (&xn)[NX]) {
-    // control squashing does not depend on the stage state: evaluate once per control set
-    const double gap = m.acc_hi - m.acc_lo;
     S delta[NSET], acc[NSET], sdel[NSET], cdel[NSET];
     double atref[NSET];
 #pragma unroll
-    for (int g = 0; g < NSET; ++g) {
-      delta[g] = ((2.0 / M_PI) * jatan(u[3 * g + 1])) * m.constrain_angle;
-      acc[g] = gap * jsigmoid((4.0 * u[3 * g]) / gap) + m.acc_lo;
-      sdel[g] = jsin(delta[g]);
-      cdel[g] = jcos(delta[g]);
-      atref[g] = val(u[3 * g + 2]);
+    for (int g = 0; g < NSET; ++g) atref[g] = val(u[3 * g + 2]);
+    {
+      MathHot mx;
+      controls<S>(mx, m, u, delta, acc, sdel, cdel);
+      if constexpr (MathHot::kFast) {
+        if (ILQC_UNLIKELY(mx.bad)) {
+          MathExact me;
+          controls<S>(me, m, u, delta, acc, sdel, cdel);
+        }
+      }
     }
-    const double Cm1 = m.Cm1, Cm2 = m.Cm2, Cr0 = m.Cr0, Cr2 = m.Cr2, Br = m.Br, Cr = m.Cr, Dr = m.Dr, Bf = m.Bf,
-                 Cf = m.Cf, Df = m.Df, mass = m.m, Iz = m.Iz, lf = m.lf, lr = m.lr;
+    const Par p = {m.Cm1, m.Cm2, m.Cr0, m.Cr2, m.Br, m.Cr, m.Dr, m.Bf, m.Cf, m.Df, m.m, m.Iz, m.lf, m.lr, 1.0 / m.m, 1.0 / m.Iz};
     const S xv[6] = {x[0], x[1], x[2], x[3], x[4], x[5]};
     S xvn[6];
     auto f = [&](int set, const S* s, S* d) {
-      const S phi = s[2], vx = s[3], vy = s[4], vphi = s[5];
-      const S alphaf = delta[set] - jatan2(vphi * lf + vy, vx);
-      const S alphar = jatan2(vphi * lr - vy, vx);
-      const S Fry = Dr * jsin(Cr * jatan(Br * alphar));
-      const S Ffy = Df * jsin(Cf * jatan(Bf * alphaf));
-      const S Frx = (Cm1 - Cm2 * vx) * acc[set] - Cr0 - Cr2 * jsq(vx);
-      const S sphi = jsin(phi), cphi = jcos(phi);
-      d[0] = cphi * vx - sphi * vy;
-      d[1] = sphi * vx + cphi * vy;
-      d[2] = vphi;
-      d[3] = (Frx - Ffy * sdel[set] + (mass * vy) * vphi) / mass;
-      d[4] = (Fry + Ffy * cdel[set] - (mass * vx) * vphi) / mass;
-      d[5] = ((Ffy * lf) * cdel[set] - Fry * lr) / Iz;
+      MathHot mx;
+      dyn<S>(mx, p, delta[set], acc[set], sdel[set], cdel[set], s, d);
+      if constexpr (MathHot::kFast) {
+        if (ILQC_UNLIKELY(mx.bad)) {  // an argument outside the fast functions' range: CUDA math library
+          MathExact me;
+          dyn<S>(me, p, delta[set], acc[set], sdel[set], cdel[set], s, d);
+        }
+      }
     };
     integrate<S, 6, VAR>(m.integrator, m.dt, f, xv, xvn);
 #pragma unroll

@@ -344,6 +344,16 @@ class Engine:
         return SolveResult(cmd=cmd_host, stepsize=stepsize_host, cost=cost, norm_grad_obj=gnorm,
                            stepsize_reported=srep, n_done=n_done, status=status)
 
+    def fastmath_eval(self, fn, a, b=None):
+        """Self-test of csrc/fastmath.cuh: fn in {sincos, atan2, atan, div, rcp, sqrt_rsqrt}, elementwise."""
+        code = ["sincos", "atan2", "atan", "div", "rcp", "sqrt_rsqrt"].index(fn)
+        a = a.to(self.device, F64).contiguous()
+        b = b.to(self.device, F64).contiguous() if b is not None else None
+        o0, o1 = torch.empty_like(a), torch.empty_like(a)
+        _lib.check(self.lib.ilqc_fastmath_eval(code, a.numel(), self._ptr(a), self._ptr(b) if b is not None else None,
+                                               self._ptr(o0), self._ptr(o1), self._stream()), "ilqc_fastmath_eval")
+        return o0, o1
+
     def fp64_peak(self, iters=4096):
         out = C.c_double()
         _lib.check(self.lib.ilqc_fp64_peak(int(iters), C.byref(out), self._stream()), "ilqc_fp64_peak")

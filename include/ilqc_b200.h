@@ -191,6 +191,12 @@ int ilqc_profile_read(double* ms, int64_t* launches, int64_t* units, int n);
 /* Number of kernels launched by this library since the last reset (all entry points, bookkeeping included). */
 long long ilqc_launch_count(int reset);
 
+/* Self-test of the device math layer (csrc/fastmath.cuh: branch-free FP64 sin/cos, atan2, atan, division,
+ * reciprocal, sqrt + 1/sqrt used by the car models in place of the CUDA math library on their stated
+ * argument ranges).  fn: 0 sincos(a) -> o0 = sin, o1 = cos ; 1 atan2(a, b) ; 2 atan(a) ; 3 a / b ; 4 1 / a ;
+ * 5 o0 = sqrt(a), o1 = 1/sqrt(a).  n elements, device pointers (b, o1 may be NULL where unused). */
+int ilqc_fastmath_eval(int fn, int n, const double* a, const double* b, double* o0, double* o1, void* stream);
+
 /* FP64 DFMA micro-benchmark used for the roofline denominator: returns achieved FLOP/s (2 per DFMA). */
 int ilqc_fp64_peak(int iters, double* flops_per_s, void* stream);
 

@@ -13,15 +13,7 @@ sys.path.insert(0, ROOT)
 from ilqc_b200 import build as b  # noqa: E402
 
 VARIANTS = {
-    "base": [],
-    "bwd6": ["-DILQC_LB_BWD=6"],
-    "bwd8": ["-DILQC_LB_BWD=8"],
-    "fwd6": ["-DILQC_LB_FWD1=6"],
-    "fwd8": ["-DILQC_LB_FWD1=8"],
-    "roll10": ["-DILQC_LB_ROLL=10"],
-    "roll6": ["-DILQC_LB_ROLL=6"],
-    "blk32": ["-DILQC_BLOCK=32", "-DILQC_LB_BWD=8", "-DILQC_LB_FWD1=8", "-DILQC_LB_ROLL=16"],
-    "blk128": ["-DILQC_BLOCK=128", "-DILQC_LB_BWD=2", "-DILQC_LB_FWD1=2", "-DILQC_LB_ROLL=4"],
+    "nofm": ["-DILQC_FASTMATH=0"],
 }
 
 
@@ -29,7 +21,7 @@ def main():
     b.build_cuda(verbose=True)
     vdir = os.path.join(b.PKG, "build", "variants")
     os.makedirs(vdir, exist_ok=True)
-    objs = [os.path.join(b.PKG, "build", f) for f in ("model_0.o", "model_1.o", "model_2.o", "dense.o", "api.o")]
+    objs = [os.path.join(b.PKG, "build", f) for f in ("model_0.o", "model_1.o", "model_2.o", "model_5.o", "model_6.o", "model_7.o", "dense.o", "api.o")]
 
     def one(item):
         tag, flags = item
