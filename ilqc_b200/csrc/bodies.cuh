@@ -136,47 +136,114 @@ ILQC_HD void forward_body(const ilqc_model_desc& m, int b, int B, const double* 
 }
 
 // ----------------------------------------------------------------------------------------------------
-// loads of the packed record into the Riccati operands
+// loads of the packed record into the Riccati operands.  `rd(slot)` returns entry `slot` of the record.
 // ----------------------------------------------------------------------------------------------------
-template <class M, class BellT>
-ILQC_HD void load_dyn(BellT& bl, const double* __restrict__ rec, int B) {
+struct GlobalRec {  // record in HBM: [component][problem], this thread's problem
+  const double* p;
+  size_t B;
+  ILQC_HD double operator()(int slot) const { return p[(size_t)slot * B]; }
+};
+template <class M, class BellT, class Rd>
+ILQC_HD void load_dyn(BellT& bl, const Rd& rd) {
   using L = Layout<M>;
   static_for<M::NX>([&](auto I) {
     constexpr int i = I;
     static_for<M::NX>([&](auto Jc) {
       constexpr int j = Jc;
-      if constexpr (M::Nm(i, j)) bl.N[i][j] = rec[(size_t)(L::oN + M::Nm.slot(i, j)) * B];
+      if constexpr (M::Nm(i, j)) bl.N[i][j] = rd(L::oN + M::Nm.slot(i, j));
     });
     static_for<M::NU>([&](auto Kc) {
       constexpr int k = Kc;
-      if constexpr (M::Bm(i, k)) bl.B[i][k] = rec[(size_t)(L::oB + M::Bm.slot(i, k)) * B];
+      if constexpr (M::Bm(i, k)) bl.B[i][k] = rd(L::oB + M::Bm.slot(i, k));
     });
   });
 }
-template <class M>
-ILQC_HD void load_state_cost(double (&p)[M::NX], double (&P)[M::NX][M::NX], const double* __restrict__ rec, int B) {
+template <class M, class Rd>
+ILQC_HD void load_state_cost(double (&p)[M::NX], double (&P)[M::NX][M::NX], const Rd& rd) {
   using L = Layout<M>;
   static_for<M::NX>([&](auto I) {
     constexpr int i = I;
-    if constexpr (M::pm(0, i)) p[i] = rec[(size_t)(L::op + M::pm.slot(0, i)) * B]; else p[i] = 0.0;
+    if constexpr (M::pm(0, i)) p[i] = rd(L::op + M::pm.slot(0, i)); else p[i] = 0.0;
     static_for<M::NX>([&](auto Jc) {
       constexpr int j = Jc;
       if constexpr (j >= i) {
-        if constexpr (M::Pm(i, j)) P[i][j] = rec[(size_t)(L::oP + M::Pm.slot(i, j)) * B]; else P[i][j] = 0.0;
+        if constexpr (M::Pm(i, j)) P[i][j] = rd(L::oP + M::Pm.slot(i, j)); else P[i][j] = 0.0;
       }
     });
   });
 }
 
+// Operand feed of the backward recursion.  Step t consumes chunk(t) = {N, B, q, Qd of record t} + {p, P of
+// record t-1} (the state cost charged on x_t), Layout<M>::stride doubles.
+//   DirectFeed: plain global loads at the point of use (test-only host build; models whose chunk does not
+//               fit the shared-memory budget).
+//   AsyncFeed : (CUDA) every thread copies ITS OWN next chunk into shared memory with cp.async while it
+//               computes the current step, double-buffered: [2][stride][block] doubles, no barrier needed
+//               because a thread only ever reads what it copied itself.  The recursion runs at the
+//               255-register limit with 8 warps per SM, so nothing else can cover the HBM latency of the
+//               ~50 dependent-free loads per step (ncu before: 3.6 of 6.5 stall cycles per issue were
+//               long_scoreboard at 47 % of the HBM peak).
+template <class M>
+struct DirectFeed {
+  const double* lin_b;  // lin + b
+  size_t B;
+  int t_cur = 0;
+  ILQC_HD void prefetch(int) {}
+  ILQC_HD void acquire(int t, bool) { t_cur = t; }
+  ILQC_HD GlobalRec dyn() const { return GlobalRec{lin_b + (size_t)t_cur * Layout<M>::stride * B, B}; }
+  ILQC_HD GlobalRec cost() const { return GlobalRec{lin_b + (size_t)(t_cur - 1) * Layout<M>::stride * B, B}; }
+};
+#if defined(__CUDA_ARCH__)
+struct SmemRec {
+  const double* p;  // this thread's column of the staged chunk: [component][block]
+  ILQC_D double operator()(int slot) const { return p[slot * ILQC_BLOCK]; }
+};
+template <class M>
+struct AsyncFeed {
+  using L = Layout<M>;
+  const double* lin_b;
+  size_t B;
+  double* sm;  // + threadIdx.x
+  int stage = 1;  // buffer holding the chunk being consumed
+  int fill = 1;   // buffer the latest prefetch went to
+  static ILQC_D void cp8(double* dst, const double* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+  }
+  // issue the copies of chunk(t) into the other buffer
+  ILQC_D void prefetch(int t) {
+    fill ^= 1;
+    double* dst = sm + (size_t)fill * L::stride * ILQC_BLOCK;
+    const double* rt = lin_b + (size_t)t * L::stride * B;
+#pragma unroll
+    for (int c = 0; c < L::op; ++c) cp8(dst + c * ILQC_BLOCK, rt + (size_t)c * B);
+    if (t > 0) {
+      const double* rp = rt - (size_t)L::stride * B;
+#pragma unroll
+      for (int c = L::op; c < L::stride; ++c) cp8(dst + c * ILQC_BLOCK, rp + (size_t)c * B);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // make chunk(t) readable: it is the older of the (at most) two groups in flight
+  ILQC_D void acquire(int, bool one_in_flight_behind) {
+    if (one_in_flight_behind) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    stage ^= 1;
+  }
+  ILQC_D SmemRec dyn() const { return SmemRec{sm + (size_t)stage * L::stride * ILQC_BLOCK}; }
+  ILQC_D SmemRec cost() const { return dyn(); }
+};
+#endif
+
 // ----------------------------------------------------------------------------------------------------
 // backward pass (MODE = ILQC_BWD_*).  slot s serves problem b with regularisation reg_ctrl.
 // gains record per step: [K row-major NU x NX | k NU], layout [t][gain_stride][n_slots]
 // ----------------------------------------------------------------------------------------------------
-template <class M, int MODE>
+template <class M, int MODE, class Feed>
 ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, int B, double reg_ctrl,
                            double reg_state, const double* __restrict__ lin, const double* __restrict__ traj,
                            const double* __restrict__ cmd, double* __restrict__ gains,
-                           double* __restrict__ jcst_out, int32_t* __restrict__ feas_out) {
+                           double* __restrict__ jcst_out, int32_t* __restrict__ feas_out, Feed& feed) {
   constexpr int NX = M::NX, NU = M::NU;
   constexpr bool QUAD = (MODE != ILQC_BWD_LINQUAD);
   using L = Layout<M>;
@@ -186,7 +253,7 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
   double J[sym_size(NX)], j[NX];
   {
     double pH[NX], PH[NX][NX];
-    load_state_cost<M>(pH, PH, lin + (size_t)(H - 1) * L::stride * B + b, B);
+    load_state_cost<M>(pH, PH, GlobalRec{lin + (size_t)(H - 1) * L::stride * B + b, (size_t)B});
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       j[i] = pH[i];
@@ -198,15 +265,20 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
 #pragma unroll
   for (int i = 0; i < NX; ++i) lam[i] = j[i];
   double jcst = 0.0;
+  feed.prefetch(H - 1);
   for (int t = H - 1; t >= 0; --t) {
-    const double* rec = lin + (size_t)t * L::stride * B + b;
-    load_dyn<M>(bl, rec, B);
+    if (t > 0) feed.prefetch(t - 1);
+    feed.acquire(t, t > 0);
+    {
+      const auto rec = feed.dyn();
+      load_dyn<M>(bl, rec);
 #pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      bl.q[u] = rec[(size_t)(L::oq + u) * B];
+      for (int u = 0; u < NU; ++u) {
+        bl.q[u] = rec(L::oq + u);
 #pragma unroll
-      for (int v = u; v < NU; ++v) bl.Q[u][v] = 0.0;
-      bl.Q[u][u] = rec[(size_t)(L::oQ + u) * B] + reg_ctrl;
+        for (int v = u; v < NU; ++v) bl.Q[u][v] = 0.0;
+        bl.Q[u][u] = rec(L::oQ + u) + reg_ctrl;
+      }
     }
     double hxx[QUAD ? sym_size(M::NV) : 1];  // state block of the dynamics Hessian, added to P in phase 2
     if constexpr (QUAD) {
@@ -265,7 +337,7 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
     // state cost on x_t (costs[t] of the reference; zero at t = 0), loaded only now to keep N, B, W and the
     // cost operands from being live at the same time
     if (t > 0) {
-      load_state_cost<M>(bl.p, bl.P, lin + (size_t)(t - 1) * L::stride * B + b, B);
+      load_state_cost<M>(bl.p, bl.P, feed.cost());
     } else {
 #pragma unroll
       for (int i = 0; i < NX; ++i) {

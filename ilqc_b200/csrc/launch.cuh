@@ -28,6 +28,7 @@ inline long long& launch_counter() { static long long n = 0; return n; }
       ILQC_UNPAREN kern(__VA_ARGS__);                            \
     }                                                            \
   } while (0)
+#define ILQC_LAUNCH_SMEM(kern, n, block, smem, stream, ...) ILQC_LAUNCH(kern, n, block, stream, __VA_ARGS__)
 #define ILQC_LAUNCH_OK() 0
 #else
 #include <cuda_runtime.h>
@@ -46,6 +47,19 @@ inline long long& launch_counter() { static long long n = 0; return n; }
       ILQC_UNPAREN kern<<<((n) + (block)-1) / (block), (block), 0, (stream)>>>(__VA_ARGS__);        \
       ++::ilqc::launch_counter();                                                                  \
     }                                                                                              \
+  } while (0)
+// same with dynamic shared memory (opt-in above 48 KB is requested once per kernel)
+#define ILQC_LAUNCH_SMEM(kern, n, block, smem, stream, ...)                                                   \
+  do {                                                                                                         \
+    if ((n) > 0) {                                                                                             \
+      static bool _attr_set = false;                                                                           \
+      if (!_attr_set && (smem) > 0) {                                                                          \
+        cudaFuncSetAttribute(ILQC_UNPAREN kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));     \
+        _attr_set = true;                                                                                      \
+      }                                                                                                        \
+      ILQC_UNPAREN kern<<<((n) + (block)-1) / (block), (block), (smem), (stream)>>>(__VA_ARGS__);               \
+      ++::ilqc::launch_counter();                                                                              \
+    }                                                                                                          \
   } while (0)
 #define ILQC_LAUNCH_OK() ((int)cudaGetLastError())
 #endif
@@ -70,6 +84,10 @@ constexpr int kBlock = ILQC_BLOCK;
 #ifndef ILQC_LB_ROLL
 #define ILQC_LB_ROLL 8
 #endif
+
+// internal flag or-ed into the backward mode: the slots map to (nearly) consecutive problems (all problems
+// active, candidates of a problem adjacent) -> the shared-memory operand feed pays off
+#define ILQC_BWD_DENSE_HINT 0x100
 
 // Per-model launchers, defined once per model in model_kernels.inl (one translation unit per model so
 // that the heavy templates compile in parallel).

@@ -22,7 +22,24 @@ ILQC_GLOBAL_LB(ILQC_LB_FWD1) forward_kernel(ilqc_model_desc m, int B, int n_thre
   forward_body<M, ORD>(m, b, B, x0, cmd, lin, traj, cost_t, total, cnorm);
 }
 
-template <class M, int MODE>
+// shared-memory budget of the double-buffered operand feed (bodies.cuh AsyncFeed): ILQC_LB_BWD resident blocks
+// of [2][stride][ILQC_BLOCK] doubles must fit in the SM's 227 KB (1 KB per block is reserved by the runtime)
+template <class M>
+constexpr bool kBwdAsyncFeed =
+#if defined(ILQC_HOSTSIM) || (defined(ILQC_BWD_ASYNC) && !ILQC_BWD_ASYNC)
+    false;
+#else
+    (size_t)ILQC_LB_BWD * (2 * Layout<M>::stride * ILQC_BLOCK * sizeof(double) + 1024) <= 227 * 1024;
+#endif
+template <class M>
+constexpr size_t kBwdSmemBytes = kBwdAsyncFeed<M> ? 2 * Layout<M>::stride * ILQC_BLOCK * sizeof(double) : 0;
+
+// ASYNC: operands staged through shared memory by cp.async (bodies.cuh AsyncFeed).  Measured on a B200
+// (profiles/r01_tuning_backward_feed.txt): 16-26 % faster than direct loads when the slots map to (nearly)
+// consecutive problems with few candidates each, i.e. the first line-search round of an iteration, and
+// slower for gathered / many-candidates-per-problem rounds (8-byte cp.async of equal or scattered addresses
+// serialises in the LSU), so the launcher picks it only for dense rounds of the linear-quadratic mode.
+template <class M, int MODE, bool ASYNC>
 ILQC_GLOBAL_LB(ILQC_LB_BWD) backward_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const int32_t* oslot,
                             int n_oslots, const double* reg_ctrl, double reg_state, const double* lin,
                             const double* traj, const double* cmd, double* gains, double* jcst, int32_t* feasible) {
@@ -30,7 +47,16 @@ ILQC_GLOBAL_LB(ILQC_LB_BWD) backward_kernel(ilqc_model_desc m, int B, int n_thre
   if (s >= n_threads) return;
   const int b = prob ? prob[s] : s;
   const int os = oslot ? oslot[s] : s;
-  backward_body<M, MODE>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, gains, jcst, feasible);
+#if defined(__CUDA_ARCH__)
+  if constexpr (ASYNC) {
+    extern __shared__ double ilqc_bwd_smem[];
+    AsyncFeed<M> feed{lin + b, (size_t)B, ilqc_bwd_smem + threadIdx.x};
+    backward_body<M, MODE>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, gains, jcst, feasible, feed);
+    return;
+  }
+#endif
+  DirectFeed<M> feed{lin + b, (size_t)B};
+  backward_body<M, MODE>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, gains, jcst, feasible, feed);
 }
 
 template <class M, int KIND>
@@ -176,14 +202,23 @@ int Launch<ILQC_MODEL_INST>::backward(int mode, const ilqc_model_desc& m, int B,
                                       const int32_t* oslot, int n_oslots, const double* reg_ctrl, double reg_state,
                                       const double* lin, const double* traj, const double* cmd, double* gains,
                                       double* jcst, int32_t* feasible, stream_t st) {
-  if (mode == ILQC_BWD_LINQUAD)
-    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_LINQUAD>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots, reg_ctrl,
+  const bool dense = (mode & ILQC_BWD_DENSE_HINT) != 0;
+  mode &= ~ILQC_BWD_DENSE_HINT;
+  if (mode == ILQC_BWD_LINQUAD) {
+    if constexpr (kBwdAsyncFeed<MI>) {
+      if (dense && n_slots <= 4 * B) {
+        ILQC_LAUNCH_SMEM((backward_kernel<MI, ILQC_BWD_LINQUAD, true>), n_slots, kBlock, kBwdSmemBytes<MI>, st, m, B, n_slots, prob,
+                         oslot, n_oslots, reg_ctrl, reg_state, lin, traj, cmd, gains, jcst, feasible);
+        return ILQC_LAUNCH_OK();
+      }
+    }
+    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_LINQUAD, false>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots, reg_ctrl,
                 reg_state, lin, traj, cmd, gains, jcst, feasible);
-  else if (mode == ILQC_BWD_QUAD_NEWTON)
-    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_NEWTON>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots,
+  } else if (mode == ILQC_BWD_QUAD_NEWTON)
+    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_NEWTON, false>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots,
                 reg_ctrl, reg_state, lin, traj, cmd, gains, jcst, feasible);
   else if (mode == ILQC_BWD_QUAD_DDP)
-    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_DDP>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots, reg_ctrl,
+    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_DDP, false>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots, reg_ctrl,
                 reg_state, lin, traj, cmd, gains, jcst, feasible);
   else
     return ILQC_E_ARG;

@@ -133,7 +133,10 @@ ILQC_HD void integrate(int integ, double dt, F&& f, const S (&x)[N], S (&xn)[N])
     // 9-12 % faster for the plain roll-out and cuts the spills of the second-order jets by a third, but is 5 %
     // slower for the first-order expansion, which keeps the unrolled form (as do the three-control-set
     // integrators, whose per-stage control set must be a compile-time index).
-    constexpr int kStageUnroll = (VAR || (is_jet<S>::value && sizeof(S) <= sizeof(double) * 16)) ? 4 : 1;
+#ifndef ILQC_STAGE_UNROLL_JET1
+#define ILQC_STAGE_UNROLL_JET1 4
+#endif
+    constexpr int kStageUnroll = VAR ? 4 : ((is_jet<S>::value && sizeof(S) <= sizeof(double) * 16) ? ILQC_STAGE_UNROLL_JET1 : 1);
     S k[N], s[N], acc[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) s[i] = x[i];

@@ -166,25 +166,38 @@ ILQC_GLOBAL compact_kernel(int B, const int32_t* flags, int32_t* list, int32_t* 
   *count = n;
 }
 #else
-__global__ void compact_kernel(int B, const int32_t* flags, int32_t* list, int32_t* count) {
-  __shared__ int sums[1024];
-  const int tid = threadIdx.x;
-  const int chunk = (B + 1023) / 1024;
-  const int lo = tid * chunk, hi = min(B, lo + chunk);
+// one block of 32 warps; warp w owns the contiguous range [w*per, (w+1)*per) and walks it 32 flags at a time
+// (coalesced loads, ballot + popc), so the list stays sorted.  pred(b) decides membership.
+template <class Pred>
+__device__ __forceinline__ void compact_block(int B, Pred pred, int32_t* list, int32_t* count) {
+  __shared__ int wsum[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int per = (((B + 31) / 32) + 31) & ~31;
+  const int lo = wid * per, hi = min(B, lo + per);
   int n = 0;
-  for (int b = lo; b < hi; ++b) n += flags[b] != 0;
-  sums[tid] = n;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const int v = (tid >= off) ? sums[tid - off] : 0;
-    __syncthreads();
-    sums[tid] += v;
-    __syncthreads();
+  for (int base = lo; base < hi; base += 32) {
+    const int b = base + lane;
+    n += __popc(__ballot_sync(0xffffffffu, b < hi && pred(b)));
   }
-  int pos = sums[tid] - n;
-  for (int b = lo; b < hi; ++b)
-    if (flags[b]) list[pos++] = b;
-  if (tid == 1023) *count = sums[1023];
+  if (lane == 0) wsum[wid] = n;
+  __syncthreads();
+  int pos = 0, total = 0;
+  for (int w = 0; w < 32; ++w) {
+    const int v = wsum[w];
+    if (w < wid) pos += v;
+    total += v;
+  }
+  for (int base = lo; base < hi; base += 32) {
+    const int b = base + lane;
+    const bool f = b < hi && pred(b);
+    const unsigned mask = __ballot_sync(0xffffffffu, f);
+    if (f) list[pos + __popc(mask & ((1u << lane) - 1u))] = b;
+    pos += __popc(mask);
+  }
+  if (threadIdx.x == 0) *count = total;
+}
+__global__ void __launch_bounds__(1024) compact_kernel(int B, const int32_t* flags, int32_t* list, int32_t* count) {
+  compact_block(B, [=](int b) { return flags[b] != 0; }, list, count);
 }
 #endif
 
@@ -300,25 +313,8 @@ ILQC_GLOBAL compact_eq_kernel(int B, const int32_t* phase, int value, int32_t* l
   *count = n;
 }
 #else
-__global__ void compact_eq_kernel(int B, const int32_t* phase, int value, int32_t* list, int32_t* count) {
-  __shared__ int sums[1024];
-  const int tid = threadIdx.x;
-  const int chunk = (B + 1023) / 1024;
-  const int lo = tid * chunk, hi = min(B, lo + chunk);
-  int n = 0;
-  for (int b = lo; b < hi; ++b) n += phase[b] == value;
-  sums[tid] = n;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const int v = (tid >= off) ? sums[tid - off] : 0;
-    __syncthreads();
-    sums[tid] += v;
-    __syncthreads();
-  }
-  int pos = sums[tid] - n;
-  for (int b = lo; b < hi; ++b)
-    if (phase[b] == value) list[pos++] = b;
-  if (tid == 1023) *count = sums[1023];
+__global__ void __launch_bounds__(1024) compact_eq_kernel(int B, const int32_t* phase, int value, int32_t* list, int32_t* count) {
+  compact_block(B, [=](int b) { return phase[b] == value; }, list, count);
 }
 #endif
 
@@ -610,7 +606,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
                                                         cmd, w.traj, w.lin, nullptr, w.dir, w.diff, w.newval, w.diffsq,
                                                         st))));
       } else if (regmode) {
-        ILQC_PROF(PROF_BACKWARD, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::backward(bwd_mode, md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
+        ILQC_PROF(PROF_BACKWARD, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::backward(bwd_mode | ((size_t)n_active * 10 >= (size_t)B * 9 ? ILQC_BWD_DENSE_HINT : 0), md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
                                                          w.gains, w.jcst, w.feas_slot, st))));
         const int kind = a->algo_type == ILQC_ALGO_DDP ? ILQC_ROLL_EXACT : ILQC_ROLL_LIN;
         ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, nullptr, n_slots, nullptr, n_slots, w.step_roll, x0, cmd,

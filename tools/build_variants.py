@@ -14,6 +14,7 @@ from ilqc_b200 import build as b  # noqa: E402
 
 VARIANTS = {
     "nofm": ["-DILQC_FASTMATH=0"],
+    "nobwdasync": ["-DILQC_BWD_ASYNC=0"],
 }
 
 

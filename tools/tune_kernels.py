@@ -46,10 +46,19 @@ def main():
         t = time_call(lambda: eng.lib.ilqc_linearize(C.byref(d), B, eng._ptr(ex["x0"]), eng._ptr(ex["cmd"]), eng._ptr(ex["lin"]),
                                                      eng._ptr(ex["traj"]), eng._ptr(ex["total"]), st))
         print(f"{tag}, linearize, {B}, {t:.3f}, {B / t:.0f}", flush=True)
-        for L in (1, 2, 3, 4):
-            n = B * L
-            prob = torch.arange(B, device="cuda", dtype=torch.int32).repeat_interleave(L).contiguous()
-            reg = (1.0 / (100.0 * 0.5 ** torch.arange(L, device="cuda", dtype=torch.float64))).repeat(B).contiguous()
+        # (active problems, candidates per problem): full waves and the straggler rounds of the line search
+        for nprob, L, order in [(B, 1, "p"), (B, 2, "p"), (B, 2, "c"), (B, 4, "p"), (B, 4, "c"), (B // 2, 4, "p"), (B // 2, 4, "c"),
+                                (B // 4, 9, "p"), (B // 4, 9, "c"), (B // 16, 32, "p"), (B // 16, 32, "c"),
+                                (B // 128, 32, "p"), (B // 128, 32, "c"), (32, 32, "p"), (32, 32, "c")]:
+            n = nprob * L
+            sel = torch.randperm(B, device="cuda")[:nprob].sort().values.to(torch.int32)
+            regs = 1.0 / (100.0 * 0.5 ** torch.arange(L, device="cuda", dtype=torch.float64))
+            if order == "p":   # problem-major: the candidates of a problem are adjacent threads
+                prob = sel.repeat_interleave(L).contiguous()
+                reg = regs.repeat(nprob).contiguous()
+            else:              # candidate-major: adjacent threads are adjacent problems
+                prob = sel.repeat(L).contiguous()
+                reg = regs.repeat_interleave(nprob).contiguous()
             gains, jcst = eng.empty(H * gstride, n), eng.empty(n)
             feas = eng.empty(n, dtype=torch.int32)
             step = torch.ones(n, device="cuda", dtype=torch.float64)
@@ -60,8 +69,8 @@ def main():
             tr = time_call(lambda: eng.lib.ilqc_rollout(C.byref(d), 0, B, n, eng._ptr(prob), None, eng._ptr(step), eng._ptr(ex["x0"]),
                                                         eng._ptr(ex["cmd"]), eng._ptr(ex["traj"]), eng._ptr(ex["lin"]), eng._ptr(gains),
                                                         None, eng._ptr(diff), eng._ptr(newval), eng._ptr(dsq), st))
-            print(f"{tag}, backward, {n}, {tb:.3f}, {n / tb:.0f}", flush=True)
-            print(f"{tag}, rollout, {n}, {tr:.3f}, {n / tr:.0f}", flush=True)
+            print(f"{tag}, backward, {nprob}x{L}{order}={n}, {tb:.3f}, {n / tb:.0f}", flush=True)
+            print(f"{tag}, rollout, {nprob}x{L}{order}={n}, {tr:.3f}, {n / tr:.0f}", flush=True)
             del gains, diff
         del eng
         torch.cuda.empty_cache()
