@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32768, help="problems per GPU")
     ap.add_argument("--iters", type=int, default=20, help="solver iterations per problem")
-    ap.add_argument("--candidates", type=int, default=32, help="max line-search candidates per problem per round")
+    ap.add_argument("--candidates", type=int, default=128, help="max line-search candidates per problem per round")
     ap.add_argument("--scheduler", type=int, default=0, help="0 auto, 1 lock-step iterations, 2 asynchronous")
     ap.add_argument("--cpu-procs", type=int, default=64)
     ap.add_argument("--ref-max-steps", type=int, default=3)

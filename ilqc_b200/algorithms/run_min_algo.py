@@ -46,7 +46,7 @@ def check_cvg_status(metrics: dict, verbose: bool = True) -> str:
 
 def run_min_algo_batched(env, max_iter: int = 10, algo: str = "ddp_linquad_reg", stepsize=None,
                          line_search: bool = True, handle_bad_dir: str = "check_total_value", x0=None,
-                         prev_cmd=None, weights=None, t0=None, batch=None, n_candidates: int = 16,
+                         prev_cmd=None, weights=None, t0=None, batch=None, n_candidates: int = 128,
                          compute_grad_norm: bool = True, engine=None):
     """B problems at once.  x0 [B,nx], prev_cmd [B,H,nu] (None: zeros), stepsize float or [B], weights [B,3]
     (Car reg_cont/reg_lag/reg_speed), t0 int or [B] (init_time_iter).  Returns ilqc_b200.engine.SolveResult

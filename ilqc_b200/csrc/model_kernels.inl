@@ -26,7 +26,7 @@ ILQC_GLOBAL_LB(ILQC_LB_FWD1) forward_kernel(ilqc_model_desc m, int B, int n_thre
 // of [2][stride][ILQC_BLOCK] doubles must fit in the SM's 227 KB (1 KB per block is reserved by the runtime)
 template <class M>
 constexpr bool kBwdAsyncFeed =
-#if defined(ILQC_HOSTSIM) || (defined(ILQC_BWD_ASYNC) && !ILQC_BWD_ASYNC)
+#if defined(ILQC_HOSTSIM)
     false;
 #else
     (size_t)ILQC_LB_BWD * (2 * Layout<M>::stride * ILQC_BLOCK * sizeof(double) + 1024) <= 227 * 1024;

@@ -482,14 +482,39 @@ inline int wave_slots() {
   return cached;
 #endif
 }
-// candidates per problem in a round with n_active searching problems (at most Lmax)
-inline int round_candidates(int n_active, int Lmax) {
-  int L = wave_slots() / (n_active > 0 ? n_active : 1);
+// ILQC_TRACE_ROUNDS=1: one stderr line per line-search round (tuning aid)
+inline bool trace_rounds() {
+  static int v = -1;
+  if (v < 0) v = getenv("ILQC_TRACE_ROUNDS") ? 1 : 0;
+  return v == 1;
+}
+// Candidates per problem in line-search round `round` (0-based) of an iteration with n_active searching
+// problems, at most Lmax (the caller's n_candidates).  Every candidate up to the accepted one has to be
+// evaluated anyway (the sequential search of the reference tries them in order), so speculation only costs
+// what lies beyond the accepted trip.  Policy from the trip statistics of the bicycle workload (trips 3-5 for
+// 92 % of the problems once the iterates settle, a 0.2 % tail of 30-110 trips) and the measured launch costs
+// (tools/sim_round_policy.py, profiles/r01_round_policy.txt):
+//   round 0: up to 4 candidates within 1.75 waves   (most problems need the first 3-4 steps 8s, 4s, 2s, s)
+//   round 1: up to 3 within one wave                (trip 5-7)
+//   round 2: up to 16 within one wave
+//   later  : up to 128 within one wave              (stragglers: finish the 30-110 halvings in one launch)
+// round < 0 (asynchronous scheduler, no round structure): one wave, Lmax.
+inline size_t round_capacity(int round) {
+  const size_t wave = (size_t)wave_slots();
+  return round == 0 ? wave + (3 * wave) / 4 : wave;
+}
+inline int round_candidates(int round, int n_active, int Lmax) {
+  static const int cap_l[4] = {4, 3, 16, 128};
+  if (round >= 0) {
+    const int c = cap_l[round < 3 ? round : 3];
+    if (c < Lmax) Lmax = c;
+  }
+  int L = (int)(round_capacity(round) / (size_t)(n_active > 0 ? n_active : 1));
   return L < 1 ? 1 : (L > Lmax ? Lmax : L);
 }
-// slots the workspace must hold: n_active * round_candidates(n_active) <= max(B, wave)
+// slots the workspace must hold: n_active * round_candidates(...) <= max(B, largest round capacity)
 inline size_t slot_capacity(int B, int Lmax) {
-  size_t cap = (size_t)B * Lmax, wave = (size_t)wave_slots();
+  size_t cap = (size_t)B * Lmax, wave = round_capacity(0);
   size_t s = cap < wave ? cap : wave;
   return s < (size_t)B ? (size_t)B : s;
 }
@@ -596,9 +621,10 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
     }
 
     // ---- line search rounds ----
-    while (n_active > 0) {
-      P.L = round_candidates(n_active, L);
+    for (int round = 0; n_active > 0; ++round) {
+      P.L = round_candidates(round, n_active, L);
       const int n_slots = n_active * P.L;
+      if (trace_rounds()) fprintf(stderr, "ilqc round: iter %d active %d candidates %d\n", it, n_active, P.L);
       ILQC_LAUNCH((make_slots_kernel), n_active, 256, st, P, n_active, w.list, w.s_try, w.prob, w.gslot, w.step_true,
                   w.step_roll, w.reg);
       if (a->algo_type == ILQC_ALGO_GD) {

@@ -110,7 +110,7 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
     }
     // ---- stream A: line-search candidates of the LS problems ----
     if (n_ls > 0) {
-      P.L = round_candidates(n_ls, L);
+      P.L = round_candidates(-1, n_ls, L);
       const int n_slots = n_ls * P.L;
       ILQC_LAUNCH((make_slots_kernel), n_ls, 256, st, P, n_ls, w.list, w.s_try, w.prob, w.gslot, w.step_true, w.step_roll, w.reg);
       if (a->algo_type == ILQC_ALGO_GD) {

@@ -288,7 +288,7 @@ class Engine:
         return self._workspace
 
     def solve(self, env, algo="ddp_linquad_reg", max_iter=10, x0=None, cmd0=None, stepsize=None, batch=None,
-              weights=None, t0=None, horizon=None, n_candidates=16, line_search=True, compute_grad_norm=True,
+              weights=None, t0=None, horizon=None, n_candidates=128, line_search=True, compute_grad_norm=True,
               record_trips=False, max_ls_trips=0, scheduler=0):
         """run_min_algo for a batch of problems of one family (device tensors in / out)."""
         if cmd0 is not None:
@@ -323,7 +323,7 @@ class Engine:
                            ls_trips=trips[:max_iter].t().contiguous() if record_trips else None)
 
     def solve_host(self, env, algo, max_iter, x0_host, cmd_host, stepsize_host, weights=None, t0=None,
-                   n_candidates=16, compute_grad_norm=True, scheduler=0):
+                   n_candidates=128, compute_grad_norm=True, scheduler=0):
         """Same solve through ilqc_solve_host: HOST (pinned) tensors in the reference layout, copies inside."""
         B, H, nu = cmd_host.shape
         d, keep = self.make_desc(env, H, B, t0, weights)

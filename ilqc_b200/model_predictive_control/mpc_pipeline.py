@@ -63,7 +63,7 @@ class MpcResult:
 
 
 def run_mpc_batched(env, full_horizon: int, window_size: int, overlap: int, max_iter: int = 10,
-                    algo: str = "ddp_linquad_reg", x0=None, weights=None, batch=None, n_candidates: int = 16,
+                    algo: str = "ddp_linquad_reg", x0=None, weights=None, batch=None, n_candidates: int = 128,
                     engine=None, max_windows: Optional[int] = None) -> MpcResult:
     """B concurrent episodes of run_mpc (mpc_pipeline.py:87-115): horizon <- min(max(horizon + window_size -
     overlap, window_size), full_horizon) per window, each window = mpc_step with the previous window's result.
