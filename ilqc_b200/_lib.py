@@ -21,6 +21,7 @@ APPROX_LINQUAD, APPROX_QUAD = 0, 1
 STEP_DIR, STEP_REG, STEP_DIRVAR, STEP_REGVAR = 0, 1, 2, 3
 RUNNING, CONVERGED, DIVERGED, STUCK, NO_DIRECTION = 0, 1, 2, 3, 4
 BWD_LINQUAD, BWD_QUAD_NEWTON, BWD_QUAD_DDP = 0, 1, 2
+BAD_DIR = {"check_total_value": 0, "flag": 1, "let_it_be": 2}
 ROLL_EXACT, ROLL_LIN, ROLL_GD = 0, 1, 2
 E_ARG, E_UNSUPPORTED, E_WORKSPACE = -1, -2, -3
 STATUS_NAMES = {RUNNING: "running", CONVERGED: "converged", DIVERGED: "diverged", STUCK: "got stuck",
@@ -49,7 +50,7 @@ class ModelDesc(C.Structure):
 class AlgoDesc(C.Structure):
     """struct ilqc_algo_desc (include/ilqc_b200.h)."""
     _fields_ = [(n, _i) for n in ("algo_type", "approx", "step_mode", "n_candidates", "line_search",
-                                  "max_ls_trips", "compute_grad_norm", "scheduler")]
+                                  "max_ls_trips", "compute_grad_norm", "scheduler", "handle_bad_dir")]
 
 
 _MP, _AP = C.POINTER(ModelDesc), C.POINTER(AlgoDesc)

@@ -53,12 +53,12 @@ def run_min_algo_batched(env, max_iter: int = 10, algo: str = "ddp_linquad_reg",
     with device tensors: cmd [B,H,nu], stepsize [B], cost / norm_grad_obj / stepsize_reported [B,max_iter+1],
     n_done [B], status [B]."""
     check_nomenclature(algo)
-    if handle_bad_dir not in ("check_total_value",):
-        raise NotImplementedError("the batched engine implements the default handle_bad_dir='check_total_value'")
+    if handle_bad_dir not in _lib.BAD_DIR:   # 'modify_hess' needs the removed torch.eig in the reference
+        raise NotImplementedError("handle_bad_dir=%r" % handle_bad_dir)
     eng = engine or default_engine()
     return eng.solve(env, algo, max_iter, x0=x0, cmd0=prev_cmd, stepsize=stepsize, batch=batch, weights=weights,
                      t0=env.init_time_iter if t0 is None else t0, n_candidates=n_candidates,
-                     line_search=line_search, compute_grad_norm=compute_grad_norm)
+                     line_search=line_search, compute_grad_norm=compute_grad_norm, handle_bad_dir=handle_bad_dir)
 
 
 def run_min_algo(env, max_iter: int = 10, algo: str = "ddp_linquad_reg", stepsize: Optional[float] = None,

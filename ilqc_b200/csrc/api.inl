@@ -134,8 +134,9 @@ int ilqc_backward(const ilqc_model_desc* m, int mode, int B, int n_slots, const 
   int rc = get_dims(m, &d);
   if (rc) return rc;
   if (B <= 0 || n_slots <= 0 || !reg_ctrl || !lin || !gains || !jcst) return ILQC_E_ARG;
-  if (mode < ILQC_BWD_LINQUAD || mode > ILQC_BWD_QUAD_DDP) return ILQC_E_ARG;
-  if (mode != ILQC_BWD_LINQUAD && (!traj || !cmd)) return ILQC_E_ARG;
+  const int flavour = mode & 0xf, bad_dir = mode >> ILQC_BWD_BAD_DIR_SHIFT;
+  if (flavour < ILQC_BWD_LINQUAD || flavour > ILQC_BWD_QUAD_DDP || bad_dir < 0 || bad_dir > ILQC_BAD_DIR_LET_IT_BE) return ILQC_E_ARG;
+  if (flavour != ILQC_BWD_LINQUAD && (!traj || !cmd)) return ILQC_E_ARG;
   ILQC_FOR_MODEL(effective_model(*m), return LM::backward(mode | (prob ? 0 : ILQC_BWD_DENSE_HINT), *m, B, n_slots, prob, nullptr, n_slots, reg_ctrl, reg_state, lin,
                                                traj, cmd, gains, jcst, feasible, (stream_t)stream));
   return 0;

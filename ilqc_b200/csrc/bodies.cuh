@@ -243,7 +243,7 @@ template <class M, int MODE, class Feed>
 ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, int B, double reg_ctrl,
                            double reg_state, const double* __restrict__ lin, const double* __restrict__ traj,
                            const double* __restrict__ cmd, double* __restrict__ gains,
-                           double* __restrict__ jcst_out, int32_t* __restrict__ feas_out, Feed& feed) {
+                           double* __restrict__ jcst_out, int32_t* __restrict__ feas_out, int bad_dir, Feed& feed) {
   constexpr int NX = M::NX, NU = M::NU;
   constexpr bool QUAD = (MODE != ILQC_BWD_LINQUAD);
   using L = Layout<M>;
@@ -261,6 +261,13 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
       for (int c = i; c < NX; ++c) J[sym_idx(i, c, NX)] = PH[i][c] + (i == c ? reg_state : 0.0);
     }
   }
+  // constant cost-Hessian entry outside the stored pattern (Car time_penalty='dref_squared', car.py:213-216)
+  double p_cross = 0.0;
+  if constexpr (M::kPassivePRow >= 0) {
+    p_cross = M::passive_P(m, load_weights(m, b, B));
+    J[sym_idx(M::kPassivePRow, M::kPassivePCol, NX)] += p_cross;
+  }
+  bool any_pos = false;  // handle_bad_dir='flag': some step had rest > 0 (backward.py:220-223)
   double lam[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) lam[i] = j[i];
@@ -369,6 +376,10 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
       }
     }
     const double rest = bl.phase2(J, j);
+    if constexpr (M::kPassivePRow >= 0) {
+      if (t > 0) J[sym_idx(M::kPassivePRow, M::kPassivePCol, NX)] += p_cross;
+    }
+    any_pos |= rest > 0.0;
     jcst = jcst + rest;
     double* g = gains + (size_t)t * L::gain_stride * n_slots + s;
 #pragma unroll
@@ -388,7 +399,13 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
   jcst_out[s] = jcst;
   // handle_bad_dir == 'check_total_value' (run_min_algo.py:21): linquad is always feasible,
   // the quad variants require a negative model decrease (backward.py:130-131)
-  if (feas_out) feas_out[s] = QUAD ? (jcst < 0.0 ? 1 : 0) : 1;
+  // 'flag': infeasible as soon as one step is non-convex; 'let_it_be': always feasible
+  if (feas_out) {
+    int feas = QUAD ? (jcst < 0.0 ? 1 : 0) : 1;
+    if (bad_dir == ILQC_BAD_DIR_FLAG) feas = any_pos ? 0 : 1;
+    else if (bad_dir == ILQC_BAD_DIR_LET_IT_BE) feas = 1;
+    feas_out[s] = feas;
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------

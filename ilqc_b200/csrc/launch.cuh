@@ -88,6 +88,8 @@ constexpr int kBlock = ILQC_BLOCK;
 // internal flag or-ed into the backward mode: the slots map to (nearly) consecutive problems (all problems
 // active, candidates of a problem adjacent) -> the shared-memory operand feed pays off
 #define ILQC_BWD_DENSE_HINT 0x100
+// bits 4-5 of the backward mode: handle_bad_dir (ILQC_BAD_DIR_*)
+#define ILQC_BWD_BAD_DIR_SHIFT 4
 
 // Per-model launchers, defined once per model in model_kernels.inl (one translation unit per model so
 // that the heavy templates compile in parallel).

@@ -42,7 +42,7 @@ constexpr size_t kBwdSmemBytes = kBwdAsyncFeed<M> ? 2 * Layout<M>::stride * ILQC
 template <class M, int MODE, bool ASYNC>
 ILQC_GLOBAL_LB(ILQC_LB_BWD) backward_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const int32_t* oslot,
                             int n_oslots, const double* reg_ctrl, double reg_state, const double* lin,
-                            const double* traj, const double* cmd, double* gains, double* jcst, int32_t* feasible) {
+                            const double* traj, const double* cmd, double* gains, double* jcst, int32_t* feasible, int bad_dir) {
   const int s = ILQC_TID;
   if (s >= n_threads) return;
   const int b = prob ? prob[s] : s;
@@ -51,12 +51,12 @@ ILQC_GLOBAL_LB(ILQC_LB_BWD) backward_kernel(ilqc_model_desc m, int B, int n_thre
   if constexpr (ASYNC) {
     extern __shared__ double ilqc_bwd_smem[];
     AsyncFeed<M> feed{lin + b, (size_t)B, ilqc_bwd_smem + threadIdx.x};
-    backward_body<M, MODE>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, gains, jcst, feasible, feed);
+    backward_body<M, MODE>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir, feed);
     return;
   }
 #endif
   DirectFeed<M> feed{lin + b, (size_t)B};
-  backward_body<M, MODE>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, gains, jcst, feasible, feed);
+  backward_body<M, MODE>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir, feed);
 }
 
 template <class M, int KIND>
@@ -118,6 +118,10 @@ ILQC_GLOBAL expand_dense_kernel(ilqc_model_desc m, int B, const double* x0, cons
         double pv = 0.0;
         if constexpr (j >= i) { if constexpr (M::Pm(i, j)) pv = rec[L::oP + M::Pm.slot(i, j)]; }
         else { if constexpr (M::Pm(j, i)) pv = rec[L::oP + M::Pm.slot(j, i)]; }
+        if constexpr (M::kPassivePRow >= 0) {
+          if ((i == M::kPassivePRow && j == M::kPassivePCol) || (j == M::kPassivePRow && i == M::kPassivePCol))
+            pv += M::passive_P(m, w);
+        }
         P[(((size_t)(t + 1) * NX + i) * NX + j) * B + b] = pv;
       });
       static_for<NU>([&](auto Kc) {
@@ -203,23 +207,24 @@ int Launch<ILQC_MODEL_INST>::backward(int mode, const ilqc_model_desc& m, int B,
                                       const double* lin, const double* traj, const double* cmd, double* gains,
                                       double* jcst, int32_t* feasible, stream_t st) {
   const bool dense = (mode & ILQC_BWD_DENSE_HINT) != 0;
-  mode &= ~ILQC_BWD_DENSE_HINT;
+  const int bad_dir = (mode >> ILQC_BWD_BAD_DIR_SHIFT) & 3;
+  mode &= 0xf;
   if (mode == ILQC_BWD_LINQUAD) {
     if constexpr (kBwdAsyncFeed<MI>) {
       if (dense && n_slots <= 4 * B) {
         ILQC_LAUNCH_SMEM((backward_kernel<MI, ILQC_BWD_LINQUAD, true>), n_slots, kBlock, kBwdSmemBytes<MI>, st, m, B, n_slots, prob,
-                         oslot, n_oslots, reg_ctrl, reg_state, lin, traj, cmd, gains, jcst, feasible);
+                         oslot, n_oslots, reg_ctrl, reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir);
         return ILQC_LAUNCH_OK();
       }
     }
     ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_LINQUAD, false>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots, reg_ctrl,
-                reg_state, lin, traj, cmd, gains, jcst, feasible);
+                reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir);
   } else if (mode == ILQC_BWD_QUAD_NEWTON)
     ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_NEWTON, false>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots,
-                reg_ctrl, reg_state, lin, traj, cmd, gains, jcst, feasible);
+                reg_ctrl, reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir);
   else if (mode == ILQC_BWD_QUAD_DDP)
     ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_DDP, false>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots, reg_ctrl,
-                reg_state, lin, traj, cmd, gains, jcst, feasible);
+                reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir);
   else
     return ILQC_E_ARG;
   return ILQC_LAUNCH_OK();

@@ -253,6 +253,8 @@ struct Model<ILQC_MODEL_PENDULUM> {
   static constexpr auto Pm = upper_of(full_mask<NX, NX>());
   static ILQC_HD double passive_N(const ilqc_model_desc&, int, int) { return 0.0; }
   static ILQC_HD double passive_B(const ilqc_model_desc&, int, int) { return 0.0; }
+  static constexpr int kPassivePRow = -1, kPassivePCol = -1;  // no constant cost-Hessian entry outside Pm
+  static ILQC_HD double passive_P(const ilqc_model_desc&, const Weights&) { return 0.0; }
 
   // dyn (pendulum.py:56-66) + euler
   template <class S>
@@ -294,6 +296,8 @@ struct CartPoleT {
   static constexpr auto Pm = parse_mask<NX, NX>("x.../.x../..../...x");
   static ILQC_HD double passive_N(const ilqc_model_desc&, int, int) { return 0.0; }
   static ILQC_HD double passive_B(const ilqc_model_desc&, int, int) { return 0.0; }
+  static constexpr int kPassivePRow = -1, kPassivePCol = -1;
+  static ILQC_HD double passive_P(const ilqc_model_desc&, const Weights&) { return 0.0; }
 
   // dyn (pendulum.py:180-198), literal ordering: unpack (x, xdot, th, thdot) = s0..s3, return
   // (xdot, thdot, dxdot, dthdot)
@@ -428,6 +432,12 @@ ILQC_HD S car_state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x
     }
   }
   return c;
+}
+
+// time_penalty='dref_squared' (car.py:213-216): -((reg_speed * vtref) * dt) * tref has the constant mixed second
+// derivative -(reg_speed * dt) wrt (tref, vtref), an entry outside the stored P pattern
+ILQC_HD double car_passive_P(const ilqc_model_desc& m, const Weights& w) {
+  return (m.cost == ILQC_COST_CONTOURING && m.time_penalty == ILQC_TP_DREF_SQUARED) ? -(w.reg_speed * m.dt) : 0.0;
 }
 
 // reg_ctrl * ctrl.dot(ctrl), or the tuple form reg[0]*(acc^2 + delta^2) + reg[1]*atref^2 summed over the
@@ -566,6 +576,8 @@ struct CarSimpleT {
     xn[5] = make_cst<S>(vn);
   }
   // constant-coefficient part of (N, B) that the jets do not carry
+  static constexpr int kPassivePRow = 4, kPassivePCol = 5;
+  static ILQC_HD double passive_P(const ilqc_model_desc& m, const Weights& w) { return car_passive_P(m, w); }
   static ILQC_HD double passive_N(const ilqc_model_desc& m, int i, int j) { return (i == 4 && j == 5) ? m.dt : 0.0; }
   static ILQC_HD double passive_B(const ilqc_model_desc& m, int i, int k) {
     if (k % 3 != 2 || i < 4) return 0.0;
@@ -683,6 +695,8 @@ struct CarBicycleT {
     xn[6] = make_cst<S>(tn);
     xn[7] = make_cst<S>(vn);
   }
+  static constexpr int kPassivePRow = 6, kPassivePCol = 7;
+  static ILQC_HD double passive_P(const ilqc_model_desc& m, const Weights& w) { return car_passive_P(m, w); }
   static ILQC_HD double passive_N(const ilqc_model_desc& m, int i, int j) { return (i == 6 && j == 7) ? m.dt : 0.0; }
   static ILQC_HD double passive_B(const ilqc_model_desc& m, int i, int k) {
     if (k % 3 != 2 || i < 6) return 0.0;

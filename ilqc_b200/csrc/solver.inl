@@ -117,8 +117,6 @@ inline int get_dims(const ilqc_model_desc* m, Dims* d) {
   if (!m) return ILQC_E_ARG;
   if (m->integrator < ILQC_INT_EULER || m->integrator > ILQC_INT_RK4) return ILQC_E_ARG;
   if (m->integrator == ILQC_INT_RK4 && m->model == ILQC_MODEL_PENDULUM) return ILQC_E_UNSUPPORTED;  // Pendulum is Euler only (pendulum.py:68-71)
-  if (m->model >= ILQC_MODEL_CAR_SIMPLE && m->cost == ILQC_COST_CONTOURING && m->time_penalty == ILQC_TP_DREF_SQUARED)
-    return ILQC_E_UNSUPPORTED;  // adds a (tref,vtref) cross term outside the stored pattern
   ILQC_FOR_MODEL(effective_model(*m), LM::dims(&d->nx, &d->nu, &d->lin_stride, &d->gain_stride));
   return 0;
 }
@@ -561,8 +559,10 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
   P.rho = regmode ? 0.5 : 0.9;
   const int max_trips = a->max_ls_trips > 0 ? a->max_ls_trips : 2000;
   const bool quad = a->approx == ILQC_APPROX_QUAD && a->algo_type != ILQC_ALGO_GD;
-  const int bwd_mode = !quad ? ILQC_BWD_LINQUAD
-                             : (a->algo_type == ILQC_ALGO_DDP ? ILQC_BWD_QUAD_DDP : ILQC_BWD_QUAD_NEWTON);
+  if (a->handle_bad_dir < ILQC_BAD_DIR_CHECK_TOTAL || a->handle_bad_dir > ILQC_BAD_DIR_LET_IT_BE) return ILQC_E_ARG;
+  const int bwd_mode = (!quad ? ILQC_BWD_LINQUAD
+                              : (a->algo_type == ILQC_ALGO_DDP ? ILQC_BWD_QUAD_DDP : ILQC_BWD_QUAD_NEWTON)) |
+                       (a->handle_bad_dir << ILQC_BWD_BAD_DIR_SHIFT);
   const bool need_grad = a->compute_grad_norm || a->algo_type == ILQC_ALGO_GD;
   const ilqc_model_desc& md = *m;
 
@@ -603,7 +603,8 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
         // slot == problem for these gains: thread a serves problem plist[a] and writes slot plist[a]
         ILQC_PROF(PROF_BACKWARD, n_pass, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::backward(bwd_mode, md, B, n_pass, plist, plist, B, w.reg_prob, 0.0, w.lin,
                                                          w.traj, cmd, w.gains, w.dec_unit, w.feas_prob, st))));
-        if (!quad) break;
+        // always feasible: linear-quadratic passes unless 'flag', every pass under 'let_it_be'
+        if ((!quad && a->handle_bad_dir != ILQC_BAD_DIR_FLAG) || a->handle_bad_dir == ILQC_BAD_DIR_LET_IT_BE) break;
         ILQC_LAUNCH((escalate_kernel), B, 256, st, B, status, w.feas_prob, w.reg_prob, w.flags);
         ILQC_LAUNCH((compact_kernel), 1, 1024, st, B, w.flags, w.ident, w.count);
         ILQC_CHECK(dev_d2h_sync(&n_pass, w.count, sizeof(int), st));

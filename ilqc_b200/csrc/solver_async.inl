@@ -62,8 +62,10 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
   P.rho = 0.5;
   const int max_trips = a->max_ls_trips > 0 ? a->max_ls_trips : 2000;
   const bool quad = a->approx == ILQC_APPROX_QUAD && a->algo_type != ILQC_ALGO_GD;
-  const int bwd_mode = !quad ? ILQC_BWD_LINQUAD
-                             : (a->algo_type == ILQC_ALGO_DDP ? ILQC_BWD_QUAD_DDP : ILQC_BWD_QUAD_NEWTON);
+  if (a->handle_bad_dir < ILQC_BAD_DIR_CHECK_TOTAL || a->handle_bad_dir > ILQC_BAD_DIR_LET_IT_BE) return ILQC_E_ARG;
+  const int bwd_mode = (!quad ? ILQC_BWD_LINQUAD
+                              : (a->algo_type == ILQC_ALGO_DDP ? ILQC_BWD_QUAD_DDP : ILQC_BWD_QUAD_NEWTON)) |
+                       (a->handle_bad_dir << ILQC_BWD_BAD_DIR_SHIFT);
   const bool need_grad = a->compute_grad_norm || a->algo_type == ILQC_ALGO_GD;
   const ilqc_model_desc& md = *m;
   AsyncState A{w.phase, w.iter, ls_trips, n_done, cost, gnorm_out, step_rep};

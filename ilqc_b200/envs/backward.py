@@ -8,8 +8,8 @@ from .. import _lib
 
 
 def _run(traj, costs, reg_ctrl, reg_state, handle_bad_dir, mode):
-    if handle_bad_dir not in ("check_total_value", "let_it_be"):
-        raise NotImplementedError("handle_bad_dir=%r: the engine implements 'check_total_value' / 'let_it_be'" % handle_bad_dir)
+    if handle_bad_dir not in _lib.BAD_DIR:   # 'modify_hess' needs the removed torch.eig in the reference
+        raise NotImplementedError("handle_bad_dir=%r" % handle_bad_dir)
     info = getattr(traj[0], "_ilqc", None)
     if info is None:
         raise ValueError("traj must come from ilqc_b200 DiffEnv.forward(cmd, approx='linquad'|'quad')")
@@ -17,13 +17,16 @@ def _run(traj, costs, reg_ctrl, reg_state, handle_bad_dir, mode):
     eng = env._engine()
     H = info["cmd"].shape[0]
     ex = eng.linearize(env, info["x0"], info["cmd"].reshape(1, H, -1), t0=info["t0"])
-    bw = eng.backward(ex, mode, torch.tensor([[float(reg_ctrl)]], dtype=torch.float64), reg_state=float(reg_state))
+    bw = eng.backward(ex, mode | (_lib.BAD_DIR[handle_bad_dir] << 4),
+                      torch.tensor([[float(reg_ctrl)]], dtype=torch.float64), reg_state=float(reg_state))
     K, k = bw["K"][0, 0].cpu(), bw["k"][0, 0].cpu()
     gains = [dict(gain_ctrl=K[t], offset_ctrl=k[t]) for t in range(H)]
     jcst = bw["jcst"][0, 0].cpu()
-    feasible = True
-    if mode != _lib.BWD_LINQUAD and handle_bad_dir == "check_total_value":
-        feasible = bool(jcst < 0)
+    feasible = bool(bw["feasible"][0, 0])
+    if not feasible and handle_bad_dir == "flag":
+        # the reference stops at the first non-convex step (backward.py:55-56): gains of the later steps only,
+        # next_jcst = None.  Callers only test `feasible` (algos_steps.py:140-147, :166-168)
+        jcst = None
     return gains, jcst, feasible
 
 

@@ -79,6 +79,12 @@ enum { ILQC_STEP_DIR = 0, ILQC_STEP_REG = 1, ILQC_STEP_DIRVAR = 2, ILQC_STEP_REG
 enum { ILQC_RUNNING = 0, ILQC_CONVERGED = 1, ILQC_DIVERGED = 2, ILQC_STUCK = 3, ILQC_NO_DIRECTION = 4 };
 /* backward-pass flavours (backward.py:6, :135, :144) */
 enum { ILQC_BWD_LINQUAD = 0, ILQC_BWD_QUAD_NEWTON = 1, ILQC_BWD_QUAD_DDP = 2 };
+/* handle_bad_dir of bell_step (backward.py:219-240): what a positive rest (non-convex step) does.
+ * check_total_value (run_min_algo's default): accept the step, quad flavours are feasible iff jcst < 0 ;
+ * flag: the pass is infeasible as soon as one step has rest > 0 ; let_it_be: always feasible.
+ * ('modify_hess' calls the removed torch.eig in the reference and is dead there.)
+ * For ilqc_backward the value is or-ed into `mode` as (handle_bad_dir << 4). */
+enum { ILQC_BAD_DIR_CHECK_TOTAL = 0, ILQC_BAD_DIR_FLAG = 1, ILQC_BAD_DIR_LET_IT_BE = 2 };
 /* roll-out flavours (rollout.py:8, :50 ; algos_steps.py:22-43) */
 enum { ILQC_ROLL_EXACT = 0, ILQC_ROLL_LIN = 1, ILQC_ROLL_GD = 2 };
 
@@ -90,6 +96,7 @@ typedef struct ilqc_algo_desc {
   int32_t compute_grad_norm;/* collect_info's ||grad_u f|| each iteration (run_min_algo.py:156-157) */
   int32_t scheduler;        /* 0 auto, 1 lock-step iterations, 2 asynchronous per-problem state machines
                                (regularised step modes and gd only); identical results either way */
+  int32_t handle_bad_dir;   /* ILQC_BAD_DIR_* (run_min_algo(handle_bad_dir=...), run_min_algo.py:21) */
 } ilqc_algo_desc;
 
 int ilqc_abi_version(void);

@@ -106,6 +106,8 @@ ENV_CASES = {
     # open tracks: handle_termination='repeat_end_point' -> smooth_min(t, L) (torch_spline.py:344-345)
     "bcar_line_h20": dict(env="real_car", track="line", horizon=20),
     "scar_bend_h20": dict(env="simple_car", track="bend", horizon=20, dt=0.04),
+    # time_penalty='dref_squared' (car.py:213-216): constant (tref, vtref) cross term in the cost Hessian
+    "bcar_dref2_h20": dict(env="real_car", track="simple", horizon=20, time_penalty="dref_squared"),
 }
 
 
@@ -342,7 +344,7 @@ class LSRecorder:
         algos_steps.backtracking_line_search = self.orig
 
 
-def trace_run(env, algo, n_iter, prev_cmd=None, stepsize=None):
+def trace_run(env, algo, n_iter, prev_cmd=None, stepsize=None, handle_bad_dir="check_total_value"):
     """Free-running run_min_algo, one iteration at a time through its own restart arguments
     (run_min_algo.py:50-75), recording the iterate after every iteration."""
     cmds, steps = [], []
@@ -354,7 +356,7 @@ def trace_run(env, algo, n_iter, prev_cmd=None, stepsize=None):
         for k in range(1, n_iter + 1):
             cmd, aux, metrics = rma.run_min_algo(
                 env, max_iter=k, algo=algo, stepsize=stepsize if aux is None else None,
-                prev_cmd=cmd, optim_aux_vars=aux, past_metrics=metrics)
+                handle_bad_dir=handle_bad_dir, prev_cmd=cmd, optim_aux_vars=aux, past_metrics=metrics)
             if cmd is None or metrics["iteration"][-1] < k:
                 break
             cmds.append(npf(cmd))
@@ -371,6 +373,7 @@ def trace_run(env, algo, n_iter, prev_cmd=None, stepsize=None):
         ls_initial=np.array(rec.initial[:n]), ls_accepted=np.array(rec.accepted[:n]),
         ls_trips=np.array(rec.trips[:n]), algo=np.array(algo),
         status=np.array(rma.check_cvg_status(metrics, verbose=False)),
+        handle_bad_dir=np.array(handle_bad_dir),
     )
 
 
@@ -405,6 +408,15 @@ RUNS = [
     ("bcar_complex_h40", "ddp_linquad_reg", 4),
     ("bcar_h100", "ddp_linquad_reg", 3),           # BASELINE config 4 (headline algo)
     ("bcar_h100", "ddp_quad_reg", 1),              # BASELINE config 4 (nominal algo), ~9 min
+    ("bcar_dref2_h20", "ddp_linquad_reg", 3),
+]
+# handle_bad_dir other than run_min_algo's default (backward.py:221-237): (case, algo, iters, handle_bad_dir)
+RUNS_BAD_DIR = [
+    ("pend_h100", "classic_quad_reg", 6, "flag"),
+    ("pend_h100", "ddp_quad_reg", 6, "let_it_be"),
+    ("cart_h50", "ddp_quad_reg", 5, "flag"),
+    ("cart_h50", "ddp_linquad_reg", 5, "flag"),
+    ("bcar_h25", "ddp_quad_reg", 2, "flag"),
 ]
 
 
@@ -419,6 +431,17 @@ def gen_runs(only=None):
         out["x0"] = npf(env.init_state)
         save(f"run_{case}_{algo}", **out)
         print(case, algo, "%.1fs" % (time.time() - t0), flush=True)
+
+
+def gen_runs_bad_dir():
+    for case, algo, iters, hbd in RUNS_BAD_DIR:
+        env = make_env(dict(ENV_CASES[case]))
+        t0 = time.time()
+        out = trace_run(env, algo, iters, handle_bad_dir=hbd)
+        out.update(cfg_to_arrays(ENV_CASES[case]))
+        out["x0"] = npf(env.init_state)
+        save(f"run_{case}_{algo}__{hbd}", **out)
+        print(case, algo, hbd, "%.1fs" % (time.time() - t0), out["ls_trips"], flush=True)
 
 
 def gen_runs_perturbed():
@@ -501,6 +524,10 @@ if __name__ == "__main__":
             gen_lin(only=gname[4:].split(","))
         elif gname == "lq":
             gen_lq()
+        elif gname == "baddir":
+            gen_runs_bad_dir()
+        elif gname.startswith("runs:"):
+            gen_runs(only=gname[5:].split(","))
         elif gname == "runs":
             gen_runs()
         elif gname.startswith("runs:"):

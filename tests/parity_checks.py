@@ -35,6 +35,10 @@ def cfg_of(g):
     return ast.literal_eval(str(g["env_cfg"]))
 
 
+def bad_dir_of(g):
+    return str(g["handle_bad_dir"]) if "handle_bad_dir" in g.files else "check_total_value"
+
+
 def relerr(a, b):
     a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
     b = np.asarray(b)
@@ -131,7 +135,8 @@ def check_run_teacher_forced(eng, name, max_iters=None):
     # all iterations as one batch of independent problems
     cmd0 = t64(g["cmds"][:n])
     steps = t64([first_stepsize(algo)] + list(g["stepsize_state"][:n - 1]))
-    r = eng.solve(env, algo, 1, x0=x0.expand(n, -1), cmd0=cmd0, stepsize=steps, record_trips=True)
+    r = eng.solve(env, algo, 1, x0=x0.expand(n, -1), cmd0=cmd0, stepsize=steps, record_trips=True,
+                  handle_bad_dir=bad_dir_of(g))
     out = {}
     for k in range(n):
         e_cost = abs(r.cost[k, 1].item() - g["cost"][k + 1]) / abs(g["cost"][k + 1])
@@ -152,7 +157,7 @@ def check_run_free(eng, name, tol=TOL):
     g = golden(name)
     env, algo = env_of(g), str(g["algo"])
     n = g["cmds"].shape[0] - 1
-    r = eng.solve(env, algo, n, x0=t64(g["x0"]).reshape(1, -1), record_trips=True)
+    r = eng.solve(env, algo, n, x0=t64(g["x0"]).reshape(1, -1), record_trips=True, handle_bad_dir=bad_dir_of(g))
     ec = np.abs(r.cost[0].cpu().numpy() - g["cost"]) / np.abs(g["cost"])
     assert np.all(ec < tol), (name, ec)
     assert relerr(r.cmd[0], g["cmds"][-1]) < max(tol, 1e-8), name

@@ -67,7 +67,10 @@ def test_oracle_backward_rollout(name):
 
 RUNS = ["run_pend_h100_ddp_linquad_reg", "run_pend_h100_classic_linquad_dir", "run_pend_h100_gd",
         "run_pend_h100_ddp_quad_reg", "run_pend_h100_classic_quad_dir", "run_pend_h100_ddp_linquad_dirvar",
-        "run_cart_h50_ddp_linquad_reg", "run_cart_h50_classic_linquad_reg", "run_scar_euler_exact_h50_ddp_linquad_reg"]
+        "run_cart_h50_ddp_linquad_reg", "run_cart_h50_classic_linquad_reg", "run_scar_euler_exact_h50_ddp_linquad_reg",
+        # handle_bad_dir = 'flag' / 'let_it_be' (backward.py:219-240)
+        "run_pend_h100_classic_quad_reg__flag", "run_pend_h100_ddp_quad_reg__let_it_be", "run_cart_h50_ddp_quad_reg__flag",
+        "run_cart_h50_ddp_linquad_reg__flag"]
 
 
 @pytest.mark.parametrize("name", RUNS)
@@ -77,7 +80,7 @@ def test_oracle_run(name):
     env = orc.make_env(pc.cfg_of(g))
     n = min(g["cmds"].shape[0] - 1, 4 if "scar" in name else 6)
     rec = []
-    cmd, aux, m = orc.run_min_algo(env, max_iter=n, algo=str(g["algo"]), record=rec)
+    cmd, aux, m = orc.run_min_algo(env, max_iter=n, algo=str(g["algo"]), record=rec, handle_bad_dir=pc.bad_dir_of(g))
     assert rel(torch.tensor(m["cost"]), g["cost"][:n + 1]) < 1e-9
     assert rel(torch.tensor(m["norm_grad_obj"]), g["norm_grad_obj"][:n + 1]) < 1e-7
     assert rel(torch.tensor(m["stepsize"]), g["stepsize_reported"][:n + 1]) < 1e-7
