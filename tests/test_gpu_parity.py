@@ -132,7 +132,11 @@ def test_empty_and_edge_inputs(cuda_engine):
     from ilqc_b200.envs import Pendulum, Car
     env = Pendulum(horizon=5)
     with pytest.raises(_lib.IlqcError):
-        cuda_engine.solve(Car(model="real", time_penalty="dref_squared"), "ddp_linquad_reg", 1)   # not built
+        cuda_engine.solve(env, "ddp_linquad_reg", 1, n_candidates=0)           # ILQC_E_ARG, nothing launched
+    with pytest.raises(NotImplementedError):
+        cuda_engine.solve(env, "ddp_linquad_reg", 1, handle_bad_dir="modify_hess")   # dead in the reference too
+    with pytest.raises(_lib.IlqcError):
+        cuda_engine.solve(Car(model="real"), "ddp_linquad_reg", 1, scheduler=2, handle_bad_dir="flag", n_candidates=-3)
     r = cuda_engine.solve(env, "ddp_linquad_reg", 0)       # zero iterations: metrics row 0 only
     assert r.cost.shape == (1, 1) and torch.isfinite(r.cost).all()
     r = cuda_engine.solve(Pendulum(horizon=1), "ddp_linquad_reg", 2)   # shortest horizon
