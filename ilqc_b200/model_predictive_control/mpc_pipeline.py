@@ -64,11 +64,13 @@ class MpcResult:
 
 def run_mpc_batched(env, full_horizon: int, window_size: int, overlap: int, max_iter: int = 10,
                     algo: str = "ddp_linquad_reg", x0=None, weights=None, batch=None, n_candidates: int = 128,
-                    engine=None, max_windows: Optional[int] = None) -> MpcResult:
+                    engine=None, max_windows: Optional[int] = None, optim_on_full_window: bool = False,
+                    keep_applying_last_ctrl: bool = True) -> MpcResult:
     """B concurrent episodes of run_mpc (mpc_pipeline.py:87-115): horizon <- min(max(horizon + window_size -
     overlap, window_size), full_horizon) per window, each window = mpc_step with the previous window's result.
     The first window is solved on `env.horizon` steps like the reference (run_min_algo sizes cmd from
-    env.horizon, run_min_algo.py:53)."""
+    env.horizon, run_min_algo.py:53).  `optim_on_full_window` re-optimises all `horizon` controls of every window
+    from the initial state; `keep_applying_last_ctrl=False` pads the warm start with zeros (mpc_pipeline.py:24-41)."""
     eng = engine or default_engine()
     dev = eng.device
     if x0 is None:
@@ -89,17 +91,24 @@ def run_mpc_batched(env, full_horizon: int, window_size: int, overlap: int, max_
         else:
             curr = cmd_hist.shape[1]
             extra = horizon - curr
-            init_cmd = torch.cat((cmd_hist[:, curr - overlap:], cmd_hist[:, -1:].repeat(1, extra, 1)), dim=1)
-            a = curr - overlap           # anchor index into the trajectory of cmd_hist (may be negative: Python slicing)
-            a_pos = a if a >= 0 else curr + 1 + a
-            if a_pos < k_frozen:
-                k_frozen, x_frozen = 0, x0
-            if a_pos > k_frozen:         # advance the frozen prefix with the plant = model
-                traj, _, _ = eng.rollout_cost(env, x_frozen, cmd_hist[:, k_frozen:a_pos], t0=k_frozen, weights=wts)
-                x_frozen, k_frozen = traj[:, -1].contiguous(), a_pos
-            r = run_min_algo_batched(env, max_iter, algo, x0=x_frozen, prev_cmd=init_cmd, weights=wts, t0=a,
-                                     n_candidates=n_candidates, engine=eng)
-            cmd_hist = torch.cat((cmd_hist[:, :-overlap], r.cmd), dim=1)  # prev_cmd[:-overlap] (mpc_pipeline.py:53)
+            pad = cmd_hist[:, -1:].repeat(1, extra, 1) if keep_applying_last_ctrl else cmd_hist.new_zeros(B, extra, cmd_hist.shape[2])
+            if optim_on_full_window:
+                # the env keeps its initial state and time (mpc_pipeline.py:35-36); the window is the whole horizon
+                r = run_min_algo_batched(env, max_iter, algo, x0=x0, prev_cmd=torch.cat((cmd_hist, pad), dim=1), weights=wts,
+                                         t0=0, n_candidates=n_candidates, engine=eng)
+                cmd_hist = r.cmd
+            else:
+                init_cmd = torch.cat((cmd_hist[:, curr - overlap:], pad), dim=1)
+                a = curr - overlap       # anchor index into the trajectory of cmd_hist (may be negative: Python slicing)
+                a_pos = a if a >= 0 else curr + 1 + a
+                if a_pos < k_frozen:
+                    k_frozen, x_frozen = 0, x0
+                if a_pos > k_frozen:     # advance the frozen prefix with the plant = model
+                    traj, _, _ = eng.rollout_cost(env, x_frozen, cmd_hist[:, k_frozen:a_pos], t0=k_frozen, weights=wts)
+                    x_frozen, k_frozen = traj[:, -1].contiguous(), a_pos
+                r = run_min_algo_batched(env, max_iter, algo, x0=x_frozen, prev_cmd=init_cmd, weights=wts, t0=a,
+                                         n_candidates=n_candidates, engine=eng)
+                cmd_hist = torch.cat((cmd_hist[:, :-overlap], r.cmd), dim=1)  # prev_cmd[:-overlap] (mpc_pipeline.py:53)
         costs.append(r.cost)
         stats.append(r.status)
         horizons.append(horizon)

@@ -164,6 +164,25 @@ def test_mpc_step_dropin_against_live_reference_windows(api_on_sim):
     assert torch.equal(prev, r.cmd[1].cpu())
 
 
+@pytest.mark.parametrize("variant", [dict(optim_on_full_window=True), dict(keep_applying_last_ctrl=False),
+                                     dict(window_size=12, overlap=8)])
+def test_mpc_batched_variants_equal_chained_mpc_step(api_on_sim, variant):
+    """run_mpc_batched with optim_on_full_window / keep_applying_last_ctrl=False / a sliding time > 1
+    (mpc_pipeline.py:24-41, :101-106) is bit-identical to the drop-in mpc_step chained through the host."""
+    from ilqc_b200.envs import make_env
+    from ilqc_b200.model_predictive_control import mpc_step, run_mpc_batched
+    cfg = dict(env="simple_car", track="simple", horizon=12, dt=0.04)
+    v = dict(variant)
+    window, overlap = v.pop("window_size", 12), v.pop("overlap", 11)
+    r = run_mpc_batched(make_env(cfg), full_horizon=window + 2 * (window - overlap), window_size=window, overlap=overlap,
+                        max_iter=3, batch=2, engine=api_on_sim, **v)
+    prev = None
+    for h in r.horizons:
+        prev, _ = mpc_step(make_env(cfg), full_horizon=h, overlap=overlap, max_iter=3, prev_cmd=prev, **v)
+    assert len(r.horizons) == 3 and r.cmd.shape[1] == r.horizons[-1]
+    assert torch.equal(prev, r.cmd[1].cpu())
+
+
 def test_mpc_cached_windows_teacher_forced(api_on_sim):
     """Cached complex-track MPC files of the reference (valid at HEAD): window h -> h+1 from the cached cmd_opt."""
     from ilqc_b200.envs import make_env
