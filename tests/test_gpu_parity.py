@@ -158,3 +158,104 @@ def test_solve_host_matches_device_path(cuda_engine):
 
 def test_lq_synth_dense_riccati_vs_dense_newton(cuda_engine):
     pc.check_lq_synth(cuda_engine)
+
+
+# ---- BASELINE.json configs 2, 3, 5 and the nominal algorithm of config 4 at their full per-GPU sizes ------------------
+def _rows_match_alone(eng, env, algo, n_iter, x0, idx, weights=None, **kw):
+    """Batch-composition independence: rows `idx` of the big batch == the same problems solved in a small batch."""
+    r = eng.solve(env, algo, n_iter, x0=x0, weights=weights, **kw)
+    rs = eng.solve(env, algo, n_iter, x0=x0[idx], weights=None if weights is None else weights[idx], **kw)
+    dev_idx = idx.to(r.cost.device)
+    same = lambda a, b: torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+    assert same(rs.cost, r.cost[dev_idx]) and same(rs.cmd, r.cmd[dev_idx]) and torch.equal(rs.status, r.status[dev_idx])
+    return r
+
+
+@pytest.mark.parametrize("algo", ["classic_linquad_reg", "ddp_linquad_reg"])
+def test_config2_cartpole_full_batch(cuda_engine, algo):
+    """BASELINE config 2: CartPendulum swing-up H=50, 16384 random initial states (pendulum.py:150-152), 20
+    iterations.  Oracle parity on two rows (3 iterations), row independence, finite decreasing costs."""
+    from ilqc_b200.envs import CartPendulum
+    from oracle import ilqc_oracle as orc
+    B = 16384
+    env = CartPendulum(horizon=50, dt=0.05, stay_put_time=0.6, x_limits=(-2.0, 2.0))
+    g = torch.Generator().manual_seed(1234)
+    x0 = torch.zeros(B, 4, dtype=torch.float64)
+    x0[:, 0] = torch.randn(B, generator=g, dtype=torch.float64)
+    idx = torch.tensor([0, 1, 5000, 16383])
+    r = _rows_match_alone(cuda_engine, env, algo, 20, x0, idx)
+    c = r.cost
+    first, done = c[:, 0], r.n_done.long()
+    last = c.gather(1, done.clamp(min=0).reshape(-1, 1)).reshape(-1)
+    assert torch.isfinite(first).all() and torch.isfinite(r.cmd).all()
+    assert (last <= first).float().mean() > 0.99
+    for b in (0, 16383):
+        oenv = orc.make_env(dict(env="cart_pendulum", horizon=50, dt=0.05, stay_put_time=0.6, x_limits=(-2.0, 2.0)))
+        oenv.init_state = x0[b].clone()
+        cmd, _, m = orc.run_min_algo(oenv, max_iter=3, algo=algo)
+        r3 = cuda_engine.solve(env, algo, 3, x0=x0[b:b + 1])
+        assert pc.relerr(r3.cost[0], np.array(m["cost"])) < 1e-9 and pc.relerr(r3.cmd[0], cmd.numpy()) < 1e-9
+
+
+def test_config3_simple_car_exact_full_batch(cuda_engine):
+    """BASELINE config 3: simple car, exact cost, Euler H=50, ddp_linquad_reg with 8 parallel line-search
+    candidates, batch 65536 (vinit_b = 1 + 0.01 xi on x0[3], x0[5], car.py:49-51, :88-90)."""
+    from ilqc_b200.envs import Car
+    from oracle import ilqc_oracle as orc
+    B = 65536
+    cfg = dict(env="simple_car", track="simple", cost="exact", discretization="euler", reg_bar=0.0, horizon=50, dt=0.04)
+    env = Car(model="simple", track="simple", cost="exact", discretization="euler", reg_bar=0.0, horizon=50, dt=0.04)
+    g = torch.Generator().manual_seed(1235)
+    x0 = env.init_state.reshape(1, -1).repeat(B, 1)
+    x0[:, 3] = 1.0 + 0.01 * torch.randn(B, generator=g, dtype=torch.float64)
+    x0[:, 5] = x0[:, 3]
+    idx = torch.tensor([0, 7, 40000, 65535])
+    r = _rows_match_alone(cuda_engine, env, "ddp_linquad_reg", 10, x0, idx, n_candidates=8)
+    assert torch.isfinite(r.cost[:, 0]).all() and torch.isfinite(r.cmd).all()
+    assert (r.cost[:, 3] < r.cost[:, 0]).float().mean() > 0.99
+    b = 65535
+    oenv = orc.make_env(dict(cfg, vinit=float(x0[b, 3])))
+    assert pc.relerr(oenv.init_state, x0[b].numpy()) < 1e-15
+    cmd, _, m = orc.run_min_algo(oenv, max_iter=2, algo="ddp_linquad_reg")
+    r2 = cuda_engine.solve(env, "ddp_linquad_reg", 2, x0=x0[b:b + 1], n_candidates=8)
+    assert pc.relerr(r2.cost[0], np.array(m["cost"])) < 1e-9 and pc.relerr(r2.cmd[0], cmd.numpy()) < 1e-9
+
+
+def test_config4_nominal_ddp_quad_reg_full_batch(cuda_engine):
+    """BASELINE config 4 with its nominal algorithm (ddp_quad_reg = Newton-type DDP, second-order jets in the
+    backward pass) at the per-GPU slice B = 32768, H = 100: one iteration, row independence, and the
+    reference's own first iteration for the unperturbed problem (run_bcar_h100_ddp_quad_reg golden)."""
+    env, x0, w = _bicycle_batch(32768)
+    g = pc.golden("run_bcar_h100_ddp_quad_reg")
+    x0[0] = pc.t64(g["x0"])
+    w[0] = torch.tensor([0.1, 10.0, 0.1], dtype=torch.float64)
+    idx = torch.tensor([0, 3, 20000, 32767])
+    r = _rows_match_alone(cuda_engine, env, "ddp_quad_reg", 1, x0, idx, weights=w)
+    assert torch.isfinite(r.cost).all()
+    assert pc.relerr(r.cost[0], g["cost"][:2]) < 1e-9 and pc.relerr(r.cmd[0], g["cmds"][1]) < 1e-9
+
+
+def test_config5_mpc_concurrent_episodes(cuda_engine):
+    """BASELINE config 5 per-GPU slice: 4096 concurrent closed-loop MPC episodes on the complex track (bicycle
+    model, window 40, overlap 39, 10 iterations per window), first 3 windows.  Episode 0 is the reference's
+    episode (live golden window 0), the others carry per-episode vinit / weights; episodes are independent."""
+    from ilqc_b200.envs import make_env
+    from ilqc_b200.model_predictive_control import run_mpc_batched
+    g = pc.golden("mpc_complex_live")
+    cfg = pc.cfg_of(g)
+    env = make_env(cfg)
+    B = 4096
+    gen = torch.Generator().manual_seed(1237)
+    xi = torch.randn(B, 4, generator=gen, dtype=torch.float64)
+    xi[0] = 0.0
+    x0 = env.init_state.reshape(1, -1).repeat(B, 1)
+    x0[:, 3] = x0[:, 3] + 0.01 * xi[:, 0]
+    x0[:, 7] = x0[:, 3]
+    w = torch.tensor([1.0, 1.0, 1.0], dtype=torch.float64).reshape(1, 3) + 1e-3 * xi[:, 1:]
+    r = run_mpc_batched(env, full_horizon=42, window_size=40, overlap=39, max_iter=10, x0=x0, weights=w, engine=cuda_engine)
+    assert r.horizons == [40, 41, 42] and r.cmd.shape == (B, 42, 3) and torch.isfinite(r.cmd).all()
+    assert pc.relerr(r.cost[0, 0, :6], g["cost_0"][:6]) < 1e-9
+    idx = torch.tensor([0, 9, 4095])
+    rs = run_mpc_batched(env, full_horizon=42, window_size=40, overlap=39, max_iter=10, x0=x0[idx], weights=w[idx],
+                         engine=cuda_engine)
+    assert torch.equal(rs.cmd, r.cmd[idx.to(r.cmd.device)])
