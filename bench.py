@@ -42,6 +42,14 @@ FLOPS_PER_STEP = {  # kernel class -> algorithmic flops per (slot, time step)
     "adjoint": 2 * (NX * NX + NX * NU),      # adjoint_kernel
 }
 CLASSES = ["rollout_cost", "linearize", "backward", "rollout_candidate", "adjoint"]
+# EXECUTED FP64 flops per (slot, time step) = dadd + dmul + 2 dfma thread instructions counted by ncu
+# (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on, profiles/r01_ncu_hot_kernels_v2.txt).  The convention
+# above counts a transcendental or a division as ONE flop (each is 10-40 FP64 instructions) and the Riccati step
+# as dense 8x8 algebra (the kernel skips the structural zeros), so both views are reported.
+EXEC_FLOPS_PER_STEP = {"rollout_cost": 2000, "linearize": 5941, "backward": 1495, "rollout_candidate": 2115, "adjoint": 176}
+# DRAM bytes per slot per launch of the same ncu capture (dram__bytes_read.sum + dram__bytes_write.sum of a
+# 131072-slot launch = 4 candidates for each of 32768 problems; per-problem rows are shared by the candidates)
+NCU_DRAM_BYTES_PER_SLOT = {"rollout_candidate": 26350, "backward": 31900, "linearize": 49900}
 LIN_STRIDE, GAIN_STRIDE = 52, 27
 BYTES_PER_SLOT = {  # algorithmic HBM bytes per slot per launch (H=100): reads + writes of the SoA arrays
     "rollout_cost": 8 * (NX + 100 * NU + 1),
@@ -269,12 +277,9 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel ----
-    # The timed region runs the asynchronous scheduler: candidate kernels (stream A) and expansion kernels
-    # (stream B) overlap, so an event pair around one launch also contains the other stream's work.  The
-    # per-kernel durations of the roofline therefore come from one extra solve of the same batch with the
-    # lock-step scheduler (identical kernels and results, one stream, nothing overlapped), CUDA events around
-    # every launch, right after the timed region; the event times of the timed region itself are reported as
-    # `kernels_timed_region`.
+    # Per-kernel durations: CUDA events around every launch (on the launching stream) of one extra lock-step
+    # solve of the same batch right after the timed region (`kernels`); the event times collected inside the
+    # timed region itself are reported as `kernels_timed_region`.
     lib.ilqc_profile_enable(1)
     lib.ilqc_profile_read(ms_buf, n_buf, u_buf, 8)
     eng.solve(env, ALGO, iters, x0=x0d, weights=wd, n_candidates=L, scheduler=1)
@@ -295,8 +300,19 @@ def run_ours(args):
     flops = FLOPS_PER_STEP[dom] * 100 * pd["slots"]
     achieved = flops / (pd["ms"] * 1e-3) / 1e12 if pd["ms"] > 0 else 0.0
     bytes_ = BYTES_PER_SLOT[dom] * pd["slots"]
+    exec_flops = EXEC_FLOPS_PER_STEP[dom] * 100 * pd["slots"]
+    exec_tflops = exec_flops / (pd["ms"] * 1e-3) / 1e12 if pd["ms"] > 0 else 0.0
+    traffic = NCU_DRAM_BYTES_PER_SLOT.get(dom)
     roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": peak_fp64 / 1e12, "unit": "TFLOP/s",
-                "frac": achieved / (peak_fp64 / 1e12), "traffic": None,
+                "frac": achieved / (peak_fp64 / 1e12),
+                "traffic": None if traffic is None else traffic * pd["slots"] / max(pd["launches"], 1),
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per slot (profiles/r01_ncu_hot_kernels_v2.txt) "
+                                  "x average slots per launch",
+                "algorithmic_bytes_per_launch_avg": bytes_ / max(pd["launches"], 1),
+                "executed": {"achieved": exec_tflops, "unit": "TFLOP/s", "frac": exec_tflops / (peak_fp64 / 1e12),
+                             "flops_per_slot_step": EXEC_FLOPS_PER_STEP[dom],
+                             "note": "FP64 instructions actually executed (ncu dadd + dmul + 2 dfma per slot-step) / "
+                                     "live CUDA-event time; the convention counts a transcendental as one flop"},
                 "peak_source": "measured DFMA micro-benchmark (ilqc_fp64_peak) on this GPU; nominal 37 TFLOP/s",
                 "flops_per_launch_avg": flops / max(pd["launches"], 1), "ms_per_launch_avg": pd["ms"] / max(pd["launches"], 1),
                 "share_of_kernel_time": pd["ms"] / kernel_ms_total if kernel_ms_total else None,
@@ -308,6 +324,7 @@ def run_ours(args):
     # whole-iteration algorithmic flops: F_iter formula with the measured candidates per iteration
     n_c = timed["rollout_candidate"]["slots"] / max(timed["linearize"]["slots"] - B * args.steps, 1)
     f_iter = 100 * (F_LIN + F_PHI + F_COST + n_c * (F_BELL + F_ROLL + F_COST)) + 100 * 2 * (NX * NX + NX * NU)
+    exec_total = sum(EXEC_FLOPS_PER_STEP[c] * 100 * timed[c]["slots"] for c in CLASSES)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -325,7 +342,9 @@ def run_ours(args):
         "kernels": {c: {"ms": round(p["ms"], 3), "launches": p["launches"], "slots": p["slots"]} for c, p in prof.items()},
         "kernels_timed_region": {c: {"ms": round(p["ms"], 3), "launches": p["launches"], "slots": p["slots"]} for c, p in timed.items()},
         "solver": {"candidates_per_iteration": n_c, "algorithmic_flops_per_iteration": f_iter,
-                   "algorithmic_tflops": f_iter * value / 1e12, "frac_of_fp64_peak": f_iter * value / peak_fp64},
+                   "algorithmic_tflops": f_iter * value / 1e12, "frac_of_fp64_peak": f_iter * value / peak_fp64,
+                   "executed_tflops_whole_step": exec_total * world / elapsed_s / 1e12,
+                   "executed_frac_of_fp64_peak": exec_total / elapsed_s / peak_fp64},
     }
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample ----
     if world == 1 and not args.no_cpu_baseline:
