@@ -22,6 +22,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: NCCL's version banner / debug log go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
