@@ -14,9 +14,6 @@ from ilqc_b200 import build as b  # noqa: E402
 
 VARIANTS = {
     "nofm": ["-DILQC_FASTMATH=0"],
-    "roll10": ["-DILQC_LB_ROLL=10"],
-    "roll12": ["-DILQC_LB_ROLL=12"],
-    "roll6": ["-DILQC_LB_ROLL=6"],
 }
 
 
