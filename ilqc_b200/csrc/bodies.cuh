@@ -68,23 +68,21 @@ ILQC_HD void expand_step(const ilqc_model_desc& m, const Weights& w, const doubl
       store(L::oQ + i, Qd[i]);
       gc += q[i] * q[i];
     }
-    using SC = Jet<M::NVC, 2>;
-    SC xc[NX];
-    static_for<NX>([&](auto I) { xc[I] = make_var<SC>(xn[I], M::cv(I)); });
-    const SC c = M::template state_cost<SC>(m, w, xc, time_next);
+    double cv, cg[M::NVC], ch[sym_size(M::NVC)];
+    M::cost_expansion(m, w, xn, time_next, &cv, cg, ch);
     static_for<NX>([&](auto I) {
       constexpr int i = I;
       if constexpr (M::pm(0, i)) {
-        const double v = c.g[M::cv(i)];
+        const double v = cg[M::cv(i)];
         store(L::op + M::pm.slot(0, i), v);
         gs += v * v;
       }
       static_for<NX>([&](auto Jc) {
         constexpr int j = Jc;
-        if constexpr (j >= i && M::Pm(i, j)) store(L::oP + M::Pm.slot(i, j), c.h[sym_idx(M::cv(i), M::cv(j), M::NVC)]);
+        if constexpr (j >= i && M::Pm(i, j)) store(L::oP + M::Pm.slot(i, j), ch[sym_idx(M::cv(i), M::cv(j), M::NVC)]);
       });
     });
-    *cost = c.v + cc;
+    *cost = cv + cc;
     *gsq = gc + gs;
   }
 }

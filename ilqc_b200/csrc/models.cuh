@@ -235,6 +235,21 @@ ILQC_HD S spline_deriv(const Seg& s, int spline, int ch, const S& f) {
 //   masks             N = A - I, B, p, P (upper), and for the second-order path R, Hxx, Huu
 //   step<S>()         one discrete step ; state_cost<S>() ; ctrl_cost()
 // ===================================================================================================
+// value, gradient and packed Hessian of M::state_cost wrt its NVC cost variables through second-order jets
+template <class M>
+ILQC_HD void jet_cost_expansion(const ilqc_model_desc& m, const Weights& w, const double (&x)[M::NX], int time_iter,
+                                double* cval, double (&g)[M::NVC], double (&h)[sym_size(M::NVC)]) {
+  using SC = Jet<M::NVC, 2>;
+  SC xc[M::NX];
+  static_for<M::NX>([&](auto I) { xc[I] = make_var<SC>(x[I], M::cv(I)); });
+  const SC c = M::template state_cost<SC>(m, w, xc, time_iter);
+  *cval = c.v;
+#pragma unroll
+  for (int i = 0; i < M::NVC; ++i) g[i] = c.g[i];
+#pragma unroll
+  for (int i = 0; i < sym_size(M::NVC); ++i) h[i] = c.h[i];
+}
+
 template <int MODEL>
 struct Model;
 // internal ids of the three-control-set (`rk4`) variants: public model id + ILQC_MODEL_VAR_OFFSET
@@ -272,6 +287,10 @@ struct Model<ILQC_MODEL_PENDULUM> {
   static ILQC_HD S state_cost(const ilqc_model_desc& m, const Weights&, const S (&x)[NX], int time_iter) {
     if (time_iter >= m.stay_put_start) return jsq(x[0]) + m.reg_speed * jsq(x[1]);
     return make_cst<S>(0.0);
+  }
+  static ILQC_HD void cost_expansion(const ilqc_model_desc& m, const Weights& w, const double (&x)[NX], int time_iter,
+                                     double* cval, double (&g)[NVC], double (&h)[sym_size(NVC)]) {
+    jet_cost_expansion<Model<ILQC_MODEL_PENDULUM>>(m, w, x, time_iter, cval, g, h);
   }
   static ILQC_HD double ctrl_cost(const ilqc_model_desc& m, const double (&u)[NU], double (&q)[NU],
                                   double (&Qd)[NU]) {
@@ -332,6 +351,10 @@ struct CartPoleT {
     }
     return c;
   }
+  static ILQC_HD void cost_expansion(const ilqc_model_desc& m, const Weights& w, const double (&x)[NX], int time_iter,
+                                     double* cval, double (&g)[NVC], double (&h)[sym_size(NVC)]) {
+    jet_cost_expansion<CartPoleT<VAR>>(m, w, x, time_iter, cval, g, h);
+  }
   // reg_ctrl * ctrl.dot(ctrl) (pendulum.py:217-222)
   static ILQC_HD double ctrl_cost(const ilqc_model_desc& m, const double (&u)[NU], double (&q)[NU],
                                   double (&Qd)[NU]) {
@@ -351,12 +374,18 @@ template <> struct Model<ILQC_MODEL_CARTPOLE + ILQC_MODEL_VAR_OFFSET> : CartPole
 // ---------------------------------------------------------------------------------------------------
 // Car: shared cost code (car.py:190-302).
 // ---------------------------------------------------------------------------------------------------
-template <class S, int NX, class MX>
-ILQC_HD S car_state_cost_mx(MX& mx, const ilqc_model_desc& m, const Weights& w, const S (&x)[NX]) {
-  const S& px = x[0];
-  const S& py = x[1];
-  const S& tref = x[NX - 2];
-  const S& vtref = x[NX - 1];
+// Contouring cost (car.py:196-227) + barrier (car.py:255-302) as a function of the reference time `tref`, which
+// is the only argument that enters through the splines: S = double (roll-outs) or Jet<1,2> seeded on tref (cost
+// expansion).  x, y enter through ex = x - xr(tref), ey = y - yr(tref) only (the barrier's `point` is detached,
+// car.py:262) and vtref through separable terms, so their derivatives are closed forms of the quantities
+// returned in `aux` (car_cost_expansion below) and a 4-variable second-order jet is never needed.
+template <class S>
+struct CarCostAux {
+  S ec, el, sp, cp;  // contouring / lag error and sin / cos of the track heading, as functions of tref
+};
+template <class S, class MX>
+ILQC_HD S car_contouring_cost(MX& mx, const ilqc_model_desc& m, const Weights& w, double px, double py, const S& tref,
+                              double vtref, CarCostAux<S>* aux) {
   S fr;
   const Seg sg = spline_locate<S>(m, tref, &fr);
   const S xr = spline_eval<S>(sg, 0, 0, fr), yr = spline_eval<S>(sg, 0, 1, fr);
@@ -377,15 +406,15 @@ ILQC_HD S car_state_cost_mx(MX& mx, const ilqc_model_desc& m, const Weights& w, 
   const S ex = px - xr, ey = py - yr;
   const S cont_err = sp * ex - cp * ey;
   const S lag_err = -cp * ex - sp * ey;
+  if (aux) { aux->ec = cont_err; aux->el = lag_err; aux->sp = sp; aux->cp = cp; }
   S c = w.reg_cont * jsq(cont_err) + w.reg_lag * jsq(lag_err);
   if (m.time_penalty == ILQC_TP_VREF_SQUARED) c = c + (w.reg_speed * jsq(vtref - m.vref)) * (m.dt * m.dt);
   else if (m.time_penalty == ILQC_TP_TREF) c = c - w.reg_speed * tref;
   else if (m.time_penalty == ILQC_TP_DREF) c = c - (w.reg_speed * vtref) * m.dt;
   else c = c - ((w.reg_speed * vtref) * m.dt) * tref;
   // barrier (car.py:255-302)
-  S bar = -1e-6 * mx.log(vtref);
+  S bar = make_cst<S>(-1e-6 * ::log(vtref));
   const double carwidth = 1.5 * m.car_w;
-  const double pxv = val(px), pyv = val(py);  // point = torch.tensor([x, y]) is detached (car.py:262)
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const S bx = spline_eval<S>(sg, 1 + i, 0, fr), by = spline_eval<S>(sg, 1 + i, 1, fr);
@@ -402,36 +431,100 @@ ILQC_HD S car_state_cost_mx(MX& mx, const ilqc_model_desc& m, const Weights& w, 
       n0 = val(dby) / v;
       n1 = (-val(dbx)) / v;
     }
-    const S dot = (pxv - bx) * n0 + (pyv - by) * n1;
+    const S dot = (px - bx) * n0 + (py - by) * n1;
     if (i == 0) bar = bar + m.reg_bar * jcube(jmax0(carwidth / 2.0 - dot));
     else bar = bar + m.reg_bar * jcube(jmax0(dot + carwidth / 2.0));
   }
   if (m.reg_obs > 0.0) {
-    const double d2 = (pxv - m.obs_x) * (pxv - m.obs_x) + (pyv - m.obs_y) * (pyv - m.obs_y);
+    const double d2 = (px - m.obs_x) * (px - m.obs_x) + (py - m.obs_y) * (py - m.obs_y);
     const double o = jmax0(carwidth * carwidth - d2);
     bar = bar + m.reg_obs * ((o * o) * o);
   }
   return c + bar;
 }
-template <class S, int NX>
-ILQC_HD S car_state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x)[NX], int time_iter) {
-  if (m.cost == ILQC_COST_EXACT) {
-    // time = time_iter * vref * dt is a constant of the graph (car.py:229-231)
-    const double time = ((double)time_iter * m.vref) * m.dt;
-    double fr;
-    const Seg sg = spline_locate<double>(m, time, &fr);
-    const double xr = spline_eval<double>(sg, 0, 0, fr), yr = spline_eval<double>(sg, 0, 1, fr);
-    return jsq(x[0] - xr) + jsq(x[1] - yr);
-  }
+template <class S, class MX>
+ILQC_HD S car_contouring_cost_checked(const ilqc_model_desc& m, const Weights& w, double px, double py, const S& tref,
+                                      double vtref, CarCostAux<S>* aux) {
   MathHot mx;
-  S c = car_state_cost_mx<S, NX>(mx, m, w, x);
+  S c = car_contouring_cost<S>(mx, m, w, px, py, tref, vtref, aux);
   if constexpr (MathHot::kFast) {
     if (ILQC_UNLIKELY(mx.bad)) {  // an argument outside the fast functions' range: CUDA math library
       MathExact me;
-      c = car_state_cost_mx<S, NX>(me, m, w, x);
+      c = car_contouring_cost<S>(me, m, w, px, py, tref, vtref, aux);
     }
   }
   return c;
+}
+// reference point of the `exact` cost: time = time_iter * vref * dt is a constant of the graph (car.py:229-231)
+ILQC_HD void car_exact_ref(const ilqc_model_desc& m, int time_iter, double* xr, double* yr) {
+  const double time = ((double)time_iter * m.vref) * m.dt;
+  double fr;
+  const Seg sg = spline_locate<double>(m, time, &fr);
+  *xr = spline_eval<double>(sg, 0, 0, fr);
+  *yr = spline_eval<double>(sg, 0, 1, fr);
+}
+// value of the state cost (roll-outs)
+template <class S, int NX>
+ILQC_HD S car_state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x)[NX], int time_iter) {
+  static_assert(!is_jet<S>::value, "derivatives of the car cost come from car_cost_expansion");
+  if (m.cost == ILQC_COST_EXACT) {
+    double xr, yr;
+    car_exact_ref(m, time_iter, &xr, &yr);
+    return jsq(x[0] - xr) + jsq(x[1] - yr);
+  }
+  return car_contouring_cost_checked<double, MathHot>(m, w, x[0], x[1], x[NX - 2], x[NX - 1], nullptr);
+}
+// value, gradient and Hessian of the state cost wrt the cost variables (x, y, tref, vtref) = what autograd
+// returns in the reference (forward.py:274-321): g[4], h = packed upper triangle of the 4 x 4 Hessian
+template <int NX>
+ILQC_HD void car_cost_expansion(const ilqc_model_desc& m, const Weights& w, const double (&x)[NX], int time_iter,
+                                double* cval, double (&g)[4], double (&h)[10]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) g[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) h[i] = 0.0;
+  const double px = x[0], py = x[1], tref = x[NX - 2], vtref = x[NX - 1];
+  if (m.cost == ILQC_COST_EXACT) {
+    double xr, yr;
+    car_exact_ref(m, time_iter, &xr, &yr);
+    const double ex = px - xr, ey = py - yr;
+    *cval = ex * ex + ey * ey;
+    g[0] = 2.0 * ex;
+    g[1] = 2.0 * ey;
+    h[sym_idx(0, 0, 4)] = 2.0;
+    h[sym_idx(1, 1, 4)] = 2.0;
+    return;
+  }
+  using S1 = Jet<1, 2>;
+  CarCostAux<S1> a;
+  const S1 c = car_contouring_cost_checked<S1, MathHot>(m, w, px, py, make_var<S1>(tref, 0), vtref, &a);
+  *cval = c.v;
+  const double qC = w.reg_cont, qL = w.reg_lag, qV = w.reg_speed;
+  const double sp = a.sp.v, cp = a.cp.v, dsp = a.sp.g[0], dcp = a.cp.g[0];
+  const double ec = a.ec.v, el = a.el.v, dec = a.ec.g[0], del = a.el.g[0];
+  // ec = sp ex - cp ey, el = -cp ex - sp ey  =>  d ec/dx = sp, d ec/dy = -cp, d el/dx = -cp, d el/dy = -sp
+  g[0] = 2.0 * (qC * (ec * sp) - qL * (el * cp));
+  g[1] = -2.0 * (qC * (ec * cp) + qL * (el * sp));
+  g[2] = c.g[0];
+  h[sym_idx(0, 0, 4)] = 2.0 * (qC * (sp * sp) + qL * (cp * cp));
+  h[sym_idx(1, 1, 4)] = 2.0 * (qC * (cp * cp) + qL * (sp * sp));
+  h[sym_idx(0, 1, 4)] = 2.0 * ((qL - qC) * (sp * cp));
+  h[sym_idx(0, 2, 4)] = 2.0 * (qC * (dec * sp + ec * dsp) - qL * (del * cp + el * dcp));
+  h[sym_idx(1, 2, 4)] = -2.0 * (qC * (dec * cp + ec * dcp) + qL * (del * sp + el * dsp));
+  h[sym_idx(2, 2, 4)] = c.h[0];
+  // vtref: separable terms (time penalty + log barrier)
+  const double iv = 1.0 / vtref;
+  double gv = -1e-6 * iv, hv = 1e-6 * (iv * iv);
+  if (m.time_penalty == ILQC_TP_VREF_SQUARED) {
+    gv += (2.0 * (w.reg_speed * (vtref - m.vref))) * (m.dt * m.dt);
+    hv += (2.0 * qV) * (m.dt * m.dt);
+  } else if (m.time_penalty == ILQC_TP_DREF) {
+    gv -= qV * m.dt;
+  } else if (m.time_penalty == ILQC_TP_DREF_SQUARED) {
+    gv -= (qV * m.dt) * tref;  // (the constant mixed entry -(qV dt) is car_passive_P)
+  }
+  g[3] = gv;
+  h[sym_idx(3, 3, 4)] = hv;
 }
 
 // time_penalty='dref_squared' (car.py:213-216): -((reg_speed * vtref) * dt) * tref has the constant mixed second
@@ -587,6 +680,10 @@ struct CarSimpleT {
   static ILQC_HD S state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x)[NX], int time_iter) {
     return car_state_cost<S, NX>(m, w, x, time_iter);
   }
+  static ILQC_HD void cost_expansion(const ilqc_model_desc& m, const Weights& w, const double (&x)[NX], int time_iter,
+                                     double* cval, double (&g)[NVC], double (&h)[sym_size(NVC)]) {
+    car_cost_expansion<NX>(m, w, x, time_iter, cval, g, h);
+  }
   static ILQC_HD double ctrl_cost(const ilqc_model_desc& m, const double (&u)[NU], double (&q)[NU],
                                   double (&Qd)[NU]) {
     return car_ctrl_cost<NU>(m, u, q, Qd);
@@ -705,6 +802,10 @@ struct CarBicycleT {
   template <class S>
   static ILQC_HD S state_cost(const ilqc_model_desc& m, const Weights& w, const S (&x)[NX], int time_iter) {
     return car_state_cost<S, NX>(m, w, x, time_iter);
+  }
+  static ILQC_HD void cost_expansion(const ilqc_model_desc& m, const Weights& w, const double (&x)[NX], int time_iter,
+                                     double* cval, double (&g)[NVC], double (&h)[sym_size(NVC)]) {
+    car_cost_expansion<NX>(m, w, x, time_iter, cval, g, h);
   }
   static ILQC_HD double ctrl_cost(const ilqc_model_desc& m, const double (&u)[NU], double (&q)[NU],
                                   double (&Qd)[NU]) {

@@ -108,6 +108,8 @@ ENV_CASES = {
     "scar_bend_h20": dict(env="simple_car", track="bend", horizon=20, dt=0.04),
     # time_penalty='dref_squared' (car.py:213-216): constant (tref, vtref) cross term in the cost Hessian
     "bcar_dref2_h20": dict(env="real_car", track="simple", horizon=20, time_penalty="dref_squared"),
+    "scar_tref_h20": dict(env="simple_car", track="simple", horizon=20, dt=0.04, time_penalty="tref"),
+    "bcar_dref_h20": dict(env="real_car", track="circle", horizon=20, time_penalty="dref"),
 }
 
 
