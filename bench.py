@@ -80,31 +80,53 @@ def make_batch(B, seed, H=100):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe): ONE
+    `nvidia-smi -lms 200` process, started before the warm-up (its start-up takes driver locks that stall
+    kernel launches for 100-200 ms) and killed after; only the samples that arrive between mark() and
+    __exit__ are summarised."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.samples, self.stop = index, [], False
+        self.index, self.samples, self.all_samples, self.t_mark = index, [], [], None
+        self.proc = None
         self.thread = threading.Thread(target=self.run, daemon=True)
 
     def run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([s.strip() for s in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            for line in self.proc.stdout:
+                row = [s.strip() for s in line.strip().split(",")]
+                self.all_samples.append(row)
+                if self.t_mark is not None:
+                    self.samples.append(row)
+        except Exception:
+            pass
+
+    def mark(self):
+        """start of the timed region"""
+        self.t_mark = time.time()
 
     def __enter__(self):
-        self.thread.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop = True
-        self.thread.join(timeout=6)
+        if self.proc is not None:
+            time.sleep(0.25)  # let the last sample of the region arrive
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.thread.join(timeout=5)
+        if not self.samples:  # region shorter than one sampling period: the latest sample before it ended
+            self.samples = self.all_samples[-1:]
 
     def summary(self):
         sm = sorted(float(s[0]) for s in self.samples if len(s) >= 7 and s[0].replace(".", "").isdigit())
@@ -218,27 +240,35 @@ def run_ours(args):
         return r
 
     lib = eng.lib
-    for _ in range(args.warmup):
-        r = step()
-    barrier()
-    lib.ilqc_profile_enable(1)
     ms_buf, n_buf, u_buf = (C.c_double * 8)(), (C.c_int64 * 8)(), (C.c_int64 * 8)()
-    lib.ilqc_profile_read(ms_buf, n_buf, u_buf, 8)  # reset
-    lib.ilqc_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        lib.ilqc_profile_enable(1)   # (enabled before the warm-up so that its event pool exists when timing starts)
+        for _ in range(args.warmup):
+            r = step()
+            int(r.n_done.sum().item())   # (same host-side reduction as the timed loop: its kernel loads lazily)
+        barrier()
+        lib.ilqc_profile_read(ms_buf, n_buf, u_buf, 8)  # reset
+        lib.ilqc_launch_count(1)
+        clocks.mark()
         barrier()
         e0.record()
         its = 0
+        step_ev = [e0]
         for _ in range(args.steps):
             r = step()
             its += int(r.n_done.sum().item())
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            step_ev.append(ev)
         e1.record()
         barrier()
     n_launches = int(lib.ilqc_launch_count(1))
     lib.ilqc_profile_read(ms_buf, n_buf, u_buf, 8)
     lib.ilqc_profile_enable(0)
     timed = {c: dict(ms=ms_buf[i], launches=int(n_buf[i]), slots=int(u_buf[i])) for i, c in enumerate(CLASSES)}
+    per_step_ms = [round(step_ev[i].elapsed_time(step_ev[i + 1]), 2) for i in range(args.steps)]
+    print(f"[bench] rank {rank} per-step ms: {per_step_ms}", file=sys.stderr, flush=True)
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     tot_its = torch.tensor([float(its)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -342,6 +372,7 @@ def run_ours(args):
         "gpu_launches": n_launches,
         "clocks": clocks.summary(),
         "roofline": roofline,
+        "per_step_ms": per_step_ms,
         "kernels": {c: {"ms": round(p["ms"], 3), "launches": p["launches"], "slots": p["slots"]} for c, p in prof.items()},
         "kernels_timed_region": {c: {"ms": round(p["ms"], 3), "launches": p["launches"], "slots": p["slots"]} for c, p in timed.items()},
         "solver": {"candidates_per_iteration": n_c, "algorithmic_flops_per_iteration": f_iter,
