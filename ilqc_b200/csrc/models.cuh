@@ -277,8 +277,15 @@ struct Model<ILQC_MODEL_PENDULUM> {
     const double g = m.phys[0], mm = m.phys[1], l = m.phys[2], mu = m.phys[3];
     const double c_sin = -g / l, c_fr = mu / (mm * (l * l)), c_u = 1.0 / (mm * (l * l));
     auto f = [&](int, const S* s, S* d) {
+      const S a[1] = {s[0] + M_PI};
+      S sn[1], cs[1];
+      MathHot mx;
+      mx.sincos(a, sn, cs);
+      if constexpr (MathHot::kFast) {
+        if (ILQC_UNLIKELY(mx.bad)) sn[0] = jsin(a[0]);  // |theta| >= 1e5: CUDA math library
+      }
       d[0] = s[1];
-      d[1] = c_sin * jsin(s[0] + M_PI) - c_fr * s[1] + c_u * u[0];
+      d[1] = c_sin * sn[0] - c_fr * s[1] + c_u * u[0];
     };
     integrate<S, NX, false>(m.integrator, m.dt, f, x, xn);
   }
@@ -326,17 +333,30 @@ struct CartPoleT {
     const double a11 = M + mm, a22 = I + mm * (l * l), ml = mm * l;
     const double d0 = I * (M + mm) + mm * (l * l) * M, d1 = (mm * mm) * (l * l);
     const double mgl = -mm * g * l;
-    auto f = [&](int set, const S* s, S* d) {
-      const S xdot = s[1], th = s[2], thdot = s[3];
-      const S sth = jsin(th), cth = jcos(th);
+    auto dyn = [&](auto& mx, int set, const S* s, S* d) {
+      const S xdot = s[1], thdot = s[3];
+      const S th[1] = {s[2]};
+      S sn[1], cs[1];
+      mx.sincos(th, sn, cs);
+      const S sth = sn[0], cth = cs[0];
       const S a12 = ml * cth;
       const S detA = d0 + d1 * jsq(sth);
       const S b1 = (ml * jsq(thdot)) * sth - b * xdot + u[set];
       const S b2 = mgl * sth;
       d[0] = xdot;
       d[1] = thdot;
-      d[2] = (a22 * b1 - a12 * b2) / detA;
-      d[3] = (a11 * b2 - a12 * b1) / detA;
+      d[2] = mx.div(a22 * b1 - a12 * b2, detA);
+      d[3] = mx.div(a11 * b2 - a12 * b1, detA);
+    };
+    auto f = [&](int set, const S* s, S* d) {
+      MathHot mx;
+      dyn(mx, set, s, d);
+      if constexpr (MathHot::kFast) {
+        if (ILQC_UNLIKELY(mx.bad)) {  // an argument outside the fast functions' range: CUDA math library
+          MathExact me;
+          dyn(me, set, s, d);
+        }
+      }
     };
     integrate<S, NX, VAR>(m.integrator, m.dt, f, x, xn);
   }
