@@ -46,13 +46,13 @@ FLOPS_PER_STEP = {  # kernel class -> algorithmic flops per (slot, time step)
 }
 CLASSES = ["rollout_cost", "linearize", "backward", "rollout_candidate", "adjoint"]
 # EXECUTED FP64 flops per (slot, time step) = dadd + dmul + 2 dfma thread instructions counted by ncu
-# (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on, profiles/r01_ncu_hot_kernels_v2.txt).  The convention
+# (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on, profiles/r01_ncu_hot_kernels_v3.txt).  The convention
 # above counts a transcendental or a division as ONE flop (each is 10-40 FP64 instructions) and the Riccati step
 # as dense 8x8 algebra (the kernel skips the structural zeros), so both views are reported.
-EXEC_FLOPS_PER_STEP = {"rollout_cost": 2000, "linearize": 5941, "backward": 1495, "rollout_candidate": 2115, "adjoint": 176}
+EXEC_FLOPS_PER_STEP = {"rollout_cost": 2000, "linearize": 4783, "backward": 1495, "rollout_candidate": 2115, "adjoint": 176}
 # DRAM bytes per slot per launch of the same ncu capture (dram__bytes_read.sum + dram__bytes_write.sum of a
 # 131072-slot launch = 4 candidates for each of 32768 problems; per-problem rows are shared by the candidates)
-NCU_DRAM_BYTES_PER_SLOT = {"rollout_candidate": 26350, "backward": 31900, "linearize": 49900}
+NCU_DRAM_BYTES_PER_SLOT = {"rollout_candidate": 26350, "backward": 31900, "linearize": 50100}
 LIN_STRIDE, GAIN_STRIDE = 52, 27
 BYTES_PER_SLOT = {  # algorithmic HBM bytes per slot per launch (H=100): reads + writes of the SoA arrays
     "rollout_cost": 8 * (NX + 100 * NU + 1),
@@ -339,7 +339,7 @@ def run_ours(args):
     roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": peak_fp64 / 1e12, "unit": "TFLOP/s",
                 "frac": achieved / (peak_fp64 / 1e12),
                 "traffic": None if traffic is None else traffic * pd["slots"] / max(pd["launches"], 1),
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per slot (profiles/r01_ncu_hot_kernels_v2.txt) "
+                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per slot (profiles/r01_ncu_hot_kernels_v3.txt) "
                                   "x average slots per launch",
                 "algorithmic_bytes_per_launch_avg": bytes_ / max(pd["launches"], 1),
                 "executed": {"achieved": exec_tflops, "unit": "TFLOP/s", "frac": exec_tflops / (peak_fp64 / 1e12),
