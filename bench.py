@@ -24,6 +24,8 @@ import time
 
 # stdout carries exactly one JSON line: NCCL's version banner / debug log go to stderr
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # (that level printf()s its banner to stdout)
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
