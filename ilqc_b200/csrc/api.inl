@@ -138,7 +138,7 @@ int ilqc_backward(const ilqc_model_desc* m, int mode, int B, int n_slots, const 
   if (flavour < ILQC_BWD_LINQUAD || flavour > ILQC_BWD_QUAD_DDP || bad_dir < 0 || bad_dir > ILQC_BAD_DIR_LET_IT_BE) return ILQC_E_ARG;
   if (flavour != ILQC_BWD_LINQUAD && (!traj || !cmd)) return ILQC_E_ARG;
   ILQC_FOR_MODEL(effective_model(*m), return LM::backward(mode | (prob ? 0 : ILQC_BWD_DENSE_HINT), *m, B, n_slots, prob, nullptr, n_slots, reg_ctrl, reg_state, lin,
-                                               traj, cmd, gains, jcst, feasible, (stream_t)stream));
+                                               traj, cmd, nullptr, gains, jcst, feasible, (stream_t)stream));
   return 0;
 }
 
@@ -173,7 +173,7 @@ size_t ilqc_solve_workspace_bytes(const ilqc_model_desc* m, const ilqc_algo_desc
   Dims d;
   if (get_dims(m, &d) || !a || B <= 0 || a->n_candidates < 1) return 0;
   Workspace w;
-  carve(&w, nullptr, d, m->horizon, B, a->n_candidates);
+  carve(&w, nullptr, d, m->horizon, B, a->n_candidates, needs_hess(a));
   return w.bytes;
 }
 

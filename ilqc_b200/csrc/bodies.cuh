@@ -234,13 +234,40 @@ struct AsyncFeed {
 #endif
 
 // ----------------------------------------------------------------------------------------------------
+// second-order tensor of the dynamics at (x_t, u_t) of the current iterate: packed Hessians over the NV jet
+// variables of the first NXH rows of phi, layout [t][row * sym_size(NV) + entry][problem].  One thread per
+// (problem, time step): the steps are independent once the trajectory is known.  Restates the closures
+// hess_dyn_state / hess_dyn_ctrl / hess_dyn_state_ctrl of forward.py:218-269 before their contraction with lambda.
+// ----------------------------------------------------------------------------------------------------
+template <class M>
+ILQC_HD void hess_body(const ilqc_model_desc& m, int b, int B, int t, const double* __restrict__ traj,
+                       const double* __restrict__ cmd, double* __restrict__ hess) {
+  constexpr int NX = M::NX, NU = M::NU, NH = sym_size(M::NV);
+  using S = Jet<M::NV, 2>;
+  double x[NX], u[NU];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = traj[((size_t)t * NX + i) * B + b];
+#pragma unroll
+  for (int k = 0; k < NU; ++k) u[k] = cmd[((size_t)t * NU + k) * B + b];
+  S xs[NX], us[NU], xns[NX];
+  static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], M::sv(I)); });
+  static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], M::uv(I)); });
+  M::template step<S>(m, xs, us, xns);
+  double* T = hess + (size_t)t * Layout<M>::hess_stride * B + b;
+#pragma unroll
+  for (int i = 0; i < M::NXH; ++i)
+#pragma unroll
+    for (int e = 0; e < NH; ++e) T[(size_t)(i * NH + e) * B] = xns[i].h[e];
+}
+
+// ----------------------------------------------------------------------------------------------------
 // backward pass (MODE = ILQC_BWD_*).  slot s serves problem b with regularisation reg_ctrl.
 // gains record per step: [K row-major NU x NX | k NU], layout [t][gain_stride][n_slots]
 // ----------------------------------------------------------------------------------------------------
-template <class M, int MODE, class Feed>
+template <class M, int MODE, bool TENSOR, class Feed>
 ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, int B, double reg_ctrl,
                            double reg_state, const double* __restrict__ lin, const double* __restrict__ traj,
-                           const double* __restrict__ cmd, double* __restrict__ gains,
+                           const double* __restrict__ cmd, const double* __restrict__ hess, double* __restrict__ gains,
                            double* __restrict__ jcst_out, int32_t* __restrict__ feas_out, int bad_dir, Feed& feed) {
   constexpr int NX = M::NX, NU = M::NU;
   constexpr bool QUAD = (MODE != ILQC_BWD_LINQUAD);
@@ -287,23 +314,37 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
     }
     double hxx[QUAD ? sym_size(M::NV) : 1];  // state block of the dynamics Hessian, added to P in phase 2
     if constexpr (QUAD) {
-      // Hessian of lam^T phi at (x_t, u_t) (forward.py:218-269) by second-order jets
-      using S = Jet<M::NV, 2>;
-      double x[NX], u[NU];
+      // Hessian of lam^T phi at (x_t, u_t) (forward.py:218-269)
+      if constexpr (TENSOR) {
+        // contraction of the stored second-order tensor of the dynamics (hess_body): it depends on the
+        // iterate only, not on lambda or the regularisation, so every candidate of every round shares it
+        const double* T = hess + (size_t)t * L::hess_stride * B + b;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) x[i] = traj[((size_t)t * NX + i) * B + b];
+        for (int e = 0; e < sym_size(M::NV); ++e) {
+          double acc = 0.0;
 #pragma unroll
-      for (int k = 0; k < NU; ++k) u[k] = cmd[((size_t)t * NU + k) * B + b];
-      S xs[NX], us[NU], xns[NX];
-      static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], M::sv(I)); });
-      static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], M::uv(I)); });
-      M::template step<S>(m, xs, us, xns);
+          for (int i = 0; i < M::NXH; ++i) acc += lam[i] * T[(size_t)(i * sym_size(M::NV) + e) * B];
+          hxx[e] = acc;
+        }
+      } else {
+        // ... recomputed here by second-order jets (stand-alone ilqc_backward)
+        using S = Jet<M::NV, 2>;
+        double x[NX], u[NU];
 #pragma unroll
-      for (int e = 0; e < sym_size(M::NV); ++e) {
-        double acc = 0.0;
+        for (int i = 0; i < NX; ++i) x[i] = traj[((size_t)t * NX + i) * B + b];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) acc += lam[i] * xns[i].h[e];
-        hxx[e] = acc;
+        for (int k = 0; k < NU; ++k) u[k] = cmd[((size_t)t * NU + k) * B + b];
+        S xs[NX], us[NU], xns[NX];
+        static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], M::sv(I)); });
+        static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], M::uv(I)); });
+        M::template step<S>(m, xs, us, xns);
+#pragma unroll
+        for (int e = 0; e < sym_size(M::NV); ++e) {
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < M::NXH; ++i) acc += lam[i] * xns[i].h[e];
+          hxx[e] = acc;
+        }
       }
       static_for<NX>([&](auto I) {
         constexpr int i = I;

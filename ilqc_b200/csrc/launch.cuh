@@ -20,6 +20,8 @@ inline long long& launch_counter() { static long long n = 0; return n; }
 #define ILQC_GLOBAL static void
 #define ILQC_GLOBAL_LB(minblocks) static void
 #define ILQC_TID (::ilqc::g_sim_tid)
+#define ILQC_LOCAL_TID (::ilqc::g_sim_tid)
+#define blockIdx_x_times_blockDim() 0
 #define ILQC_UNPAREN(...) __VA_ARGS__
 #define ILQC_LAUNCH(kern, n, block, stream, ...)                 \
   do {                                                           \
@@ -40,6 +42,8 @@ inline long long& launch_counter() { static long long n = 0; return n; }
 #define ILQC_GLOBAL __global__ void
 #define ILQC_GLOBAL_LB(minblocks) __global__ void __launch_bounds__(ILQC_BLOCK, minblocks)
 #define ILQC_TID ((int)(blockIdx.x * blockDim.x + threadIdx.x))
+#define ILQC_LOCAL_TID ((long long)threadIdx.x)
+#define blockIdx_x_times_blockDim() ((long long)blockIdx.x * blockDim.x)
 #define ILQC_UNPAREN(...) __VA_ARGS__
 #define ILQC_LAUNCH(kern, n, block, stream, ...)                                                   \
   do {                                                                                             \
@@ -107,8 +111,11 @@ struct Launch {
   // stride n_oslots; roll-outs read their gains at gslot[s] (NULL: s) with stride n_gslots.
   static int backward(int mode, const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob,
                       const int32_t* oslot, int n_oslots, const double* reg_ctrl, double reg_state,
-                      const double* lin, const double* traj, const double* cmd, double* gains, double* jcst,
-                      int32_t* feasible, stream_t st);
+                      const double* lin, const double* traj, const double* cmd, const double* hess, double* gains,
+                      double* jcst, int32_t* feasible, stream_t st);
+  // second-order tensor of the dynamics of the problems prob[0..n_probs) (NULL: all), [H][hess_stride][B]
+  static int hess(const ilqc_model_desc& m, int B, int n_probs, const int32_t* prob, const double* traj,
+                  const double* cmd, double* hess, stream_t st);
   static int rollout(int kind, const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob,
                      const int32_t* gslot, int n_gslots, const int32_t* oslot, int n_oslots, const double* step,
                      const double* x0, const double* cmd, const double* traj, const double* lin,
@@ -116,7 +123,7 @@ struct Launch {
                      stream_t st);
   static int adjoint(const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob, const double* lin,
                      double* grad, double* gnorm, stream_t st);
-  static void dims(int* nx, int* nu, int* lin_stride, int* gain_stride);
+  static void dims(int* nx, int* nu, int* lin_stride, int* gain_stride, int* hess_stride);
 };
 
 }  // namespace ilqc

@@ -39,10 +39,11 @@ constexpr size_t kBwdSmemBytes = kBwdAsyncFeed<M> ? 2 * Layout<M>::stride * ILQC
 // consecutive problems with few candidates each, i.e. the first line-search round of an iteration, and
 // slower for gathered / many-candidates-per-problem rounds (8-byte cp.async of equal or scattered addresses
 // serialises in the LSU), so the launcher picks it only for dense rounds of the linear-quadratic mode.
-template <class M, int MODE, bool ASYNC>
+template <class M, int MODE, bool ASYNC, bool TENSOR>
 ILQC_GLOBAL_LB(ILQC_LB_BWD) backward_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const int32_t* oslot,
                             int n_oslots, const double* reg_ctrl, double reg_state, const double* lin,
-                            const double* traj, const double* cmd, double* gains, double* jcst, int32_t* feasible, int bad_dir) {
+                            const double* traj, const double* cmd, const double* hess, double* gains, double* jcst,
+                            int32_t* feasible, int bad_dir) {
   const int s = ILQC_TID;
   if (s >= n_threads) return;
   const int b = prob ? prob[s] : s;
@@ -51,12 +52,12 @@ ILQC_GLOBAL_LB(ILQC_LB_BWD) backward_kernel(ilqc_model_desc m, int B, int n_thre
   if constexpr (ASYNC) {
     extern __shared__ double ilqc_bwd_smem[];
     AsyncFeed<M> feed{lin + b, (size_t)B, ilqc_bwd_smem + threadIdx.x};
-    backward_body<M, MODE>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir, feed);
+    backward_body<M, MODE, TENSOR>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, hess, gains, jcst, feasible, bad_dir, feed);
     return;
   }
 #endif
   DirectFeed<M> feed{lin + b, (size_t)B};
-  backward_body<M, MODE>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir, feed);
+  backward_body<M, MODE, TENSOR>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, hess, gains, jcst, feasible, bad_dir, feed);
 }
 
 template <class M, int KIND>
@@ -71,6 +72,17 @@ ILQC_GLOBAL_LB(ILQC_LB_ROLL) rollout_kernel(ilqc_model_desc m, int B, int n_thre
   const int os = oslot ? oslot[s] : s;
   rollout_body<M, KIND>(m, os, n_oslots, b, B, gs, n_gslots, step[s], x0, cmd, traj, lin, gains, dir, diff, newval,
                         diffsq);
+}
+
+// one thread per (problem, time step); consecutive threads = consecutive problems of the same step
+template <class M>
+ILQC_GLOBAL_LB(ILQC_LB_BWD) hess_kernel(ilqc_model_desc m, int B, int n_probs, const int32_t* prob, const double* traj,
+                                        const double* cmd, double* hess) {
+  const long long i = (long long)blockIdx_x_times_blockDim() + ILQC_LOCAL_TID;
+  if (i >= (long long)n_probs * m.horizon) return;
+  const int a = (int)(i % n_probs), t = (int)(i / n_probs);
+  const int b = prob ? prob[a] : a;
+  hess_body<M>(m, b, B, t, traj, cmd, hess);
 }
 
 template <class M>
@@ -204,29 +216,39 @@ int Launch<ILQC_MODEL_INST>::expand_dense(const ilqc_model_desc& m, int B, const
 template <>
 int Launch<ILQC_MODEL_INST>::backward(int mode, const ilqc_model_desc& m, int B, int n_slots, const int32_t* prob,
                                       const int32_t* oslot, int n_oslots, const double* reg_ctrl, double reg_state,
-                                      const double* lin, const double* traj, const double* cmd, double* gains,
-                                      double* jcst, int32_t* feasible, stream_t st) {
+                                      const double* lin, const double* traj, const double* cmd, const double* hess,
+                                      double* gains, double* jcst, int32_t* feasible, stream_t st) {
   const bool dense = (mode & ILQC_BWD_DENSE_HINT) != 0;
   const int bad_dir = (mode >> ILQC_BWD_BAD_DIR_SHIFT) & 3;
   mode &= 0xf;
+#define ILQC_BWD_ARGS m, B, n_slots, prob, oslot, n_oslots, reg_ctrl, reg_state, lin, traj, cmd, hess, gains, jcst, feasible, bad_dir
   if (mode == ILQC_BWD_LINQUAD) {
     if constexpr (kBwdAsyncFeed<MI>) {
       if (dense && n_slots <= 4 * B) {
-        ILQC_LAUNCH_SMEM((backward_kernel<MI, ILQC_BWD_LINQUAD, true>), n_slots, kBlock, kBwdSmemBytes<MI>, st, m, B, n_slots, prob,
-                         oslot, n_oslots, reg_ctrl, reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir);
+        ILQC_LAUNCH_SMEM((backward_kernel<MI, ILQC_BWD_LINQUAD, true, false>), n_slots, kBlock, kBwdSmemBytes<MI>, st, ILQC_BWD_ARGS);
         return ILQC_LAUNCH_OK();
       }
     }
-    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_LINQUAD, false>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots, reg_ctrl,
-                reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir);
-  } else if (mode == ILQC_BWD_QUAD_NEWTON)
-    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_NEWTON, false>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots,
-                reg_ctrl, reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir);
-  else if (mode == ILQC_BWD_QUAD_DDP)
-    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_DDP, false>), n_slots, kBlock, st, m, B, n_slots, prob, oslot, n_oslots, reg_ctrl,
-                reg_state, lin, traj, cmd, gains, jcst, feasible, bad_dir);
-  else
+    ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_LINQUAD, false, false>), n_slots, kBlock, st, ILQC_BWD_ARGS);
+  } else if (mode == ILQC_BWD_QUAD_NEWTON) {
+    // hess != NULL: contraction of the stored second-order tensor (Launch::hess); NULL: recomputed in the kernel
+    if (hess) ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_NEWTON, false, true>), n_slots, kBlock, st, ILQC_BWD_ARGS);
+    else ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_NEWTON, false, false>), n_slots, kBlock, st, ILQC_BWD_ARGS);
+  } else if (mode == ILQC_BWD_QUAD_DDP) {
+    if (hess) ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_DDP, false, true>), n_slots, kBlock, st, ILQC_BWD_ARGS);
+    else ILQC_LAUNCH((backward_kernel<MI, ILQC_BWD_QUAD_DDP, false, false>), n_slots, kBlock, st, ILQC_BWD_ARGS);
+  } else {
     return ILQC_E_ARG;
+  }
+#undef ILQC_BWD_ARGS
+  return ILQC_LAUNCH_OK();
+}
+
+template <>
+int Launch<ILQC_MODEL_INST>::hess(const ilqc_model_desc& m, int B, int n_probs, const int32_t* prob, const double* traj,
+                                  const double* cmd, double* hess, stream_t st) {
+  const long long n = (long long)n_probs * m.horizon;
+  ILQC_LAUNCH((hess_kernel<MI>), n, kBlock, st, m, B, n_probs, prob, traj, cmd, hess);
   return ILQC_LAUNCH_OK();
 }
 
@@ -258,11 +280,12 @@ int Launch<ILQC_MODEL_INST>::adjoint(const ilqc_model_desc& m, int B, int n_thre
 }
 
 template <>
-void Launch<ILQC_MODEL_INST>::dims(int* nx, int* nu, int* lin_stride, int* gain_stride) {
+void Launch<ILQC_MODEL_INST>::dims(int* nx, int* nu, int* lin_stride, int* gain_stride, int* hess_stride) {
   *nx = MI::NX;
   *nu = MI::NU;
   *lin_stride = Layout<MI>::stride;
   *gain_stride = Layout<MI>::gain_stride;
+  *hess_stride = Layout<MI>::hess_stride;
 }
 
 }  // namespace ilqc

@@ -259,6 +259,7 @@ struct Model;
 template <>
 struct Model<ILQC_MODEL_PENDULUM> {
   static constexpr int NX = 2, NU = 1, NV = 3, NVC = 2;
+  static constexpr int NXH = NX;  // state rows whose dynamics can have non-zero second derivatives
   static constexpr int sv(int i) { constexpr int t[NX] = {0, 1}; return t[i]; }
   static constexpr int uv(int i) { constexpr int t[NU] = {2}; return t[i]; }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1}; return t[i]; }
@@ -313,6 +314,7 @@ template <bool VAR>
 struct CartPoleT {
   static constexpr int NSET = VAR ? 3 : 1;
   static constexpr int NX = 4, NU = NSET, NV = 3 + NSET, NVC = 3;
+  static constexpr int NXH = NX;
   static constexpr int sv(int i) { constexpr int t[NX] = {-1, 0, 1, 2}; return t[i]; }
   static constexpr int uv(int i) { return 3 + i; }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1, -1, 2}; return t[i]; }
@@ -613,6 +615,7 @@ struct CarSimpleT {
   // state (x, y, phi, v, tref, vtref), ctrl (a, delta, atref) per control set
   static constexpr int NSET = VAR ? 3 : 1;
   static constexpr int NX = 6, NU = 3 * NSET, NV = 2 + 2 * NSET, NVC = 4;
+  static constexpr int NXH = 4;  // (tref, vtref) evolve linearly
   static constexpr int sv(int i) { constexpr int t[NX] = {-1, -1, 0, 1, -1, -1}; return t[i]; }
   static constexpr int uv(int k) { return (k % 3 == 2) ? -1 : 2 + 2 * (k / 3) + (k % 3); }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1, -1, -1, 2, 3}; return t[i]; }
@@ -718,6 +721,7 @@ struct CarBicycleT {
   // state (x, y, phi, vx, vy, vphi, tref, vtref), ctrl (a, delta, atref) per control set
   static constexpr int NSET = VAR ? 3 : 1;
   static constexpr int NX = 8, NU = 3 * NSET, NV = 4 + 2 * NSET, NVC = 4;
+  static constexpr int NXH = 6;  // (tref, vtref) evolve linearly
   static constexpr int sv(int i) { constexpr int t[NX] = {-1, -1, 0, 1, 2, 3, -1, -1}; return t[i]; }
   static constexpr int uv(int k) { return (k % 3 == 2) ? -1 : 4 + 2 * (k / 3) + (k % 3); }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1, -1, -1, -1, -1, 2, 3}; return t[i]; }
@@ -851,6 +855,8 @@ struct Layout {
   static constexpr int oN = 0, oB = oN + nN, oq = oB + nB, oQ = oq + M::NU, op = oQ + M::NU, oP = op + np;
   static constexpr int stride = oP + nP;
   static constexpr int gain_stride = M::NU * M::NX + M::NU;
+  // second-order tensor of the dynamics: packed Hessians (over the NV jet variables) of the first NXH state rows
+  static constexpr int hess_stride = M::NXH * sym_size(M::NV);
   // masks of the second-order path: Hessian of lambda^T phi lives on the jet variables
   static constexpr Mask<M::NX, M::NX> hxx() {
     Mask<M::NX, M::NX> k;

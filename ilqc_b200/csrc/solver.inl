@@ -112,12 +112,12 @@ struct ProfScope {
 #define ILQC_PROF(cls, units, stmt) do { prof.begin(cls, units); stmt; prof.end(); } while (0)
 #define ILQC_PROF_ON(stream, cls, units, stmt) do { prof.begin_on(cls, units, stream); stmt; prof.end(); } while (0)
 
-struct Dims { int nx, nu, lin_stride, gain_stride; };
+struct Dims { int nx, nu, lin_stride, gain_stride, hess_stride; };
 inline int get_dims(const ilqc_model_desc* m, Dims* d) {
   if (!m) return ILQC_E_ARG;
   if (m->integrator < ILQC_INT_EULER || m->integrator > ILQC_INT_RK4) return ILQC_E_ARG;
   if (m->integrator == ILQC_INT_RK4 && m->model == ILQC_MODEL_PENDULUM) return ILQC_E_UNSUPPORTED;  // Pendulum is Euler only (pendulum.py:68-71)
-  ILQC_FOR_MODEL(effective_model(*m), LM::dims(&d->nx, &d->nu, &d->lin_stride, &d->gain_stride));
+  ILQC_FOR_MODEL(effective_model(*m), LM::dims(&d->nx, &d->nu, &d->lin_stride, &d->gain_stride, &d->hess_stride));
   return 0;
 }
 
@@ -448,7 +448,7 @@ ILQC_GLOBAL from_soa_kernel(const double* src, double* dst, int B, int n) {
 
 // ---- workspace ----------------------------------------------------------------------------------------
 struct Workspace {
-  double *lin, *traj, *gains, *diff, *dir, *newval, *diffsq, *jcst, *step_true, *step_roll, *reg, *curr_val,
+  double *lin, *traj, *hess, *gains, *diff, *dir, *newval, *diffsq, *jcst, *step_true, *step_roll, *reg, *curr_val,
       *cnorm, *gnorm, *s_try, *dec_unit, *reg_prob;
   int32_t *prob, *gslot, *feas_slot, *feas_prob, *list, *flags, *trips, *count, *ident, *accept, *phase, *iter;
   size_t bytes;
@@ -516,13 +516,16 @@ inline size_t slot_capacity(int B, int Lmax) {
   size_t s = cap < wave ? cap : wave;
   return s < (size_t)B ? (size_t)B : s;
 }
-inline void carve(Workspace* w, char* base, const Dims& d, int H, int B, int L) {
+// quad: second-order algorithms also keep the second-order tensor of the dynamics [H][hess_stride][B]
+inline bool needs_hess(const ilqc_algo_desc* a) { return a->approx == ILQC_APPROX_QUAD && a->algo_type != ILQC_ALGO_GD; }
+inline void carve(Workspace* w, char* base, const Dims& d, int H, int B, int L, bool quad) {
   size_t off = 0;
   auto takeD = [&](size_t n) { double* p = (double*)(base + off); off = align_up(off + n * sizeof(double)); return p; };
   auto takeI = [&](size_t n) { int32_t* p = (int32_t*)(base + off); off = align_up(off + n * sizeof(int32_t)); return p; };
   const size_t S = slot_capacity(B, L);
   w->lin = takeD((size_t)H * d.lin_stride * B);
   w->traj = takeD((size_t)(H + 1) * d.nx * B);
+  w->hess = quad ? takeD((size_t)H * d.hess_stride * B) : nullptr;
   w->gains = takeD((size_t)H * d.gain_stride * S);
   w->diff = takeD((size_t)H * d.nu * S);
   w->dir = takeD((size_t)H * d.nu * B);
@@ -547,7 +550,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
   if (!a || B <= 0 || n_iter < 0 || a->n_candidates < 1) return ILQC_E_ARG;
   const int H = m->horizon, L = a->n_candidates;
   Workspace w;
-  carve(&w, (char*)workspace, d, H, B, L);
+  carve(&w, (char*)workspace, d, H, B, L, needs_hess(a));
   if (!workspace || workspace_bytes < w.bytes) return ILQC_E_WORKSPACE;
 
   ProfScope prof(st);
@@ -577,6 +580,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
   // expansion and the metrics row 0 (run_min_algo.py:65-76)
   ILQC_PROF(PROF_FORWARD0, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(0, md, B, B, nullptr, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st))));
   ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
+  if (quad) ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, B, nullptr, w.traj, cmd, w.hess, st)));
   if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
   ILQC_LAUNCH((status_kernel), B, 256, st, P, B, 0, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
               n_done);
@@ -602,7 +606,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
       for (int esc = 0; esc < 16 && n_pass > 0; ++esc) {
         // slot == problem for these gains: thread a serves problem plist[a] and writes slot plist[a]
         ILQC_PROF(PROF_BACKWARD, n_pass, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::backward(bwd_mode, md, B, n_pass, plist, plist, B, w.reg_prob, 0.0, w.lin,
-                                                         w.traj, cmd, w.gains, w.dec_unit, w.feas_prob, st))));
+                                                         w.traj, cmd, w.hess, w.gains, w.dec_unit, w.feas_prob, st))));
         // always feasible: linear-quadratic passes unless 'flag', every pass under 'let_it_be'
         if ((!quad && a->handle_bad_dir != ILQC_BAD_DIR_FLAG) || a->handle_bad_dir == ILQC_BAD_DIR_LET_IT_BE) break;
         ILQC_LAUNCH((escalate_kernel), B, 256, st, B, status, w.feas_prob, w.reg_prob, w.flags);
@@ -634,7 +638,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
                                                         st))));
       } else if (regmode) {
         ILQC_PROF(PROF_BACKWARD, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::backward(bwd_mode | ((size_t)n_active * 10 >= (size_t)B * 9 ? ILQC_BWD_DENSE_HINT : 0), md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
-                                                         w.gains, w.jcst, w.feas_slot, st))));
+                                                         w.hess, w.gains, w.jcst, w.feas_slot, st))));
         const int kind = a->algo_type == ILQC_ALGO_DDP ? ILQC_ROLL_EXACT : ILQC_ROLL_LIN;
         ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, nullptr, n_slots, nullptr, n_slots, w.step_roll, x0, cmd,
                                                         w.traj, w.lin, w.gains, nullptr, w.diff, w.newval, w.diffsq,
@@ -655,6 +659,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
 
     // re-expand at the accepted controls (algos_steps.py:376-378) and collect the metrics of this iteration
     ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
+  if (quad) ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, B, nullptr, w.traj, cmd, w.hess, st)));
     if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
     ILQC_LAUNCH((status_kernel), B, 256, st, P, B, it, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
                 n_done);

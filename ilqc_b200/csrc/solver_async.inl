@@ -49,7 +49,7 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
   if (!a || B <= 0 || n_iter < 0 || a->n_candidates < 1) return ILQC_E_ARG;
   const int H = m->horizon, L = a->n_candidates;
   Workspace w;
-  carve(&w, (char*)workspace, d, H, B, L);
+  carve(&w, (char*)workspace, d, H, B, L, needs_hess(a));
   if (!workspace || workspace_bytes < w.bytes) return ILQC_E_WORKSPACE;
 
   ProfScope prof(st);
@@ -106,6 +106,7 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
     // ---- stream B: re-expansion, gradient, metrics row and next line-search set-up of the LIN problems ----
     if (n_lin > 0) {
       ILQC_PROF_ON(sb, PROF_LINEARIZE, n_lin, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, n_lin, w.ident, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, sb))));
+      if (quad) ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, n_lin, w.ident, w.traj, cmd, w.hess, sb)));
       if (need_grad) ILQC_PROF_ON(sb, PROF_ADJOINT, n_lin, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, n_lin, w.ident, w.lin, w.dir, w.gnorm, sb))));
       ILQC_LAUNCH((status_async_kernel), n_lin, 256, sb, P, n_lin, w.ident, B, n_iter, w.curr_val, w.gnorm, w.cnorm, stepsize,
                   w.s_try, w.dec_unit, w.trips, status, A);
@@ -120,7 +121,7 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
                                                         cmd, w.traj, w.lin, nullptr, w.dir, w.diff, w.newval, w.diffsq, st))));
       } else {
         ILQC_PROF(PROF_BACKWARD, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::backward(bwd_mode, md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
-                                                         w.gains, w.jcst, w.feas_slot, st))));
+                                                         w.hess, w.gains, w.jcst, w.feas_slot, st))));
         const int kind = a->algo_type == ILQC_ALGO_DDP ? ILQC_ROLL_EXACT : ILQC_ROLL_LIN;
         ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, nullptr, n_slots, nullptr, n_slots, w.step_roll, x0, cmd,
                                                         w.traj, w.lin, w.gains, nullptr, w.diff, w.newval, w.diffsq, st))));
