@@ -236,14 +236,14 @@ struct AsyncFeed {
 // ----------------------------------------------------------------------------------------------------
 // second-order tensor of the dynamics at (x_t, u_t) of the current iterate: packed Hessians over the NV jet
 // variables of the first NXH rows of phi, layout [t][row * sym_size(NV) + entry][problem].  One thread per
-// (problem, time step): the steps are independent once the trajectory is known.  Restates the closures
+// (problem, time step, group of Hessian entries): the steps are independent once the trajectory is known.  Restates the closures
 // hess_dyn_state / hess_dyn_ctrl / hess_dyn_state_ctrl of forward.py:218-269 before their contraction with lambda.
 // ----------------------------------------------------------------------------------------------------
-template <class M>
+template <class M, int NG, int G>
 ILQC_HD void hess_body(const ilqc_model_desc& m, int b, int B, int t, const double* __restrict__ traj,
                        const double* __restrict__ cmd, double* __restrict__ hess) {
   constexpr int NX = M::NX, NU = M::NU, NH = sym_size(M::NV);
-  using S = Jet<M::NV, 2>;
+  using S = Jet<M::NV, 2, NG, G>;  // group G of NG groups of Hessian entries (jet.cuh)
   double x[NX], u[NU];
 #pragma unroll
   for (int i = 0; i < NX; ++i) x[i] = traj[((size_t)t * NX + i) * B + b];
@@ -257,7 +257,8 @@ ILQC_HD void hess_body(const ilqc_model_desc& m, int b, int B, int t, const doub
 #pragma unroll
   for (int i = 0; i < M::NXH; ++i)
 #pragma unroll
-    for (int e = 0; e < NH; ++e) T[(size_t)(i * NH + e) * B] = xns[i].h[e];
+    for (int k = 0; k < S::NH; ++k)
+      if (S::valid(k)) T[(size_t)(i * NH + S::entry(k)) * B] = xns[i].h[k];
 }
 
 // ----------------------------------------------------------------------------------------------------

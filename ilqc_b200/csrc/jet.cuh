@@ -12,17 +12,36 @@
 
 namespace ilqc {
 
-template <int N, int ORD>
+// (i, j) of the packed upper-triangle index e of a symmetric matrix of order N
+template <int N>
+struct SymTable {
+  int i[sym_size(N) > 0 ? sym_size(N) : 1], j[sym_size(N) > 0 ? sym_size(N) : 1];
+  constexpr SymTable() : i{}, j{} {
+    int e = 0;
+    for (int a = 0; a < N; ++a)
+      for (int b = a; b < N; ++b) { i[e] = a; j[e] = b; ++e; }
+  }
+};
+// NG > 1: the Hessian entries are split into NG groups of NHG consecutive packed entries and this jet carries
+// group G only (value and gradient are complete).  Every Hessian entry propagates independently given the
+// gradients, so NG threads with jets of NG-times fewer second-order components compute one full Hessian
+// (hess_kernel: the 28-double jets of the bicycle model spill 9.6 KB per thread, the 14-double ones do not).
+template <int N, int ORD, int NG = 1, int G = 0>
 struct Jet {
   static constexpr int NV = N;
-  static constexpr int NH = (ORD >= 2) ? sym_size(N) : 1;
+  static constexpr int NHG = (sym_size(N) + NG - 1) / NG;  // entries per group
+  static constexpr int NH = (ORD >= 2) ? NHG : 1;
+  static constexpr int E0 = G * NHG;                       // first packed entry of this group
   double v;
   double g[N];
   double h[NH];
+  // packed index of local entry k, and whether it exists (the last group may be padded)
+  static constexpr int entry(int k) { return E0 + k; }
+  static constexpr bool valid(int k) { return E0 + k < sym_size(N); }
 };
 
 template <class S> struct is_jet : std::false_type {};
-template <int N, int O> struct is_jet<Jet<N, O>> : std::true_type {};
+template <int N, int O, int NG, int G> struct is_jet<Jet<N, O, NG, G>> : std::true_type {};
 
 // ---- construction ------------------------------------------------------------------------------------
 template <class S>
@@ -51,130 +70,136 @@ ILQC_HD S make_var(double v, int idx) {  // idx < 0: unseeded constant
   }
 }
 ILQC_HD double val(double a) { return a; }
-template <int N, int O> ILQC_HD double val(const Jet<N, O>& a) { return a.v; }
+template <int N, int O, int NG, int G> ILQC_HD double val(const Jet<N, O, NG, G>& a) { return a.v; }
 ILQC_HD void set_val(double& a, double v) { a = v; }
-template <int N, int O> ILQC_HD void set_val(Jet<N, O>& a, double v) { a.v = v; }
+template <int N, int O, int NG, int G> ILQC_HD void set_val(Jet<N, O, NG, G>& a, double v) { a.v = v; }
 // autograd's .detach()/torch.tensor(x): keep the value, drop the derivatives (envs/car.py:262, :267)
 template <class S> ILQC_HD S detach(const S& a) { return make_cst<S>(val(a)); }
 
 // ---- generic chain rules -----------------------------------------------------------------------------
-template <int N, int O>
-ILQC_HD Jet<N, O> chain1(const Jet<N, O>& a, double f0, double f1, double f2) {
-  Jet<N, O> r;
+template <int N, int O, int NG, int G>
+ILQC_HD Jet<N, O, NG, G> chain1(const Jet<N, O, NG, G>& a, double f0, double f1, double f2) {
+  Jet<N, O, NG, G> r;
   r.v = f0;
 #pragma unroll
   for (int i = 0; i < N; ++i) r.g[i] = f1 * a.g[i];
   if constexpr (O >= 2) {
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = i; j < N; ++j) {
-        const int k = sym_idx(i, j, N);
+    using J = Jet<N, O, NG, G>;
+    static_for<J::NH>([&](auto K) {
+      constexpr int k = K;
+      if constexpr (J::valid(k)) {
+        constexpr int i = SymTable<N>().i[J::entry(k)], j = SymTable<N>().j[J::entry(k)];
         r.h[k] = f1 * a.h[k] + f2 * (a.g[i] * a.g[j]);
+      } else {
+        r.h[k] = 0.0;
       }
+    });
   }
   return r;
 }
-template <int N, int O>
-ILQC_HD Jet<N, O> chain2(const Jet<N, O>& a, const Jet<N, O>& b, double f0, double fa, double fb, double faa,
+template <int N, int O, int NG, int G>
+ILQC_HD Jet<N, O, NG, G> chain2(const Jet<N, O, NG, G>& a, const Jet<N, O, NG, G>& b, double f0, double fa, double fb, double faa,
                          double fab, double fbb) {
-  Jet<N, O> r;
+  Jet<N, O, NG, G> r;
   r.v = f0;
 #pragma unroll
   for (int i = 0; i < N; ++i) r.g[i] = fa * a.g[i] + fb * b.g[i];
   if constexpr (O >= 2) {
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = i; j < N; ++j) {
-        const int k = sym_idx(i, j, N);
+    using J = Jet<N, O, NG, G>;
+    static_for<J::NH>([&](auto K) {
+      constexpr int k = K;
+      if constexpr (J::valid(k)) {
+        constexpr int i = SymTable<N>().i[J::entry(k)], j = SymTable<N>().j[J::entry(k)];
         r.h[k] = fa * a.h[k] + fb * b.h[k] + faa * (a.g[i] * a.g[j]) + fbb * (b.g[i] * b.g[j]) +
                  fab * (a.g[i] * b.g[j] + a.g[j] * b.g[i]);
+      } else {
+        r.h[k] = 0.0;
       }
+    });
   }
   return r;
 }
 
 // ---- arithmetic --------------------------------------------------------------------------------------
-template <int N, int O>
-ILQC_HD Jet<N, O> operator+(const Jet<N, O>& a, const Jet<N, O>& b) {
-  Jet<N, O> r;
+template <int N, int O, int NG, int G>
+ILQC_HD Jet<N, O, NG, G> operator+(const Jet<N, O, NG, G>& a, const Jet<N, O, NG, G>& b) {
+  Jet<N, O, NG, G> r;
   r.v = a.v + b.v;
 #pragma unroll
   for (int i = 0; i < N; ++i) r.g[i] = a.g[i] + b.g[i];
   if constexpr (O >= 2) {
 #pragma unroll
-    for (int i = 0; i < Jet<N, O>::NH; ++i) r.h[i] = a.h[i] + b.h[i];
+    for (int i = 0; i < Jet<N, O, NG, G>::NH; ++i) r.h[i] = a.h[i] + b.h[i];
   }
   return r;
 }
-template <int N, int O>
-ILQC_HD Jet<N, O> operator-(const Jet<N, O>& a, const Jet<N, O>& b) {
-  Jet<N, O> r;
+template <int N, int O, int NG, int G>
+ILQC_HD Jet<N, O, NG, G> operator-(const Jet<N, O, NG, G>& a, const Jet<N, O, NG, G>& b) {
+  Jet<N, O, NG, G> r;
   r.v = a.v - b.v;
 #pragma unroll
   for (int i = 0; i < N; ++i) r.g[i] = a.g[i] - b.g[i];
   if constexpr (O >= 2) {
 #pragma unroll
-    for (int i = 0; i < Jet<N, O>::NH; ++i) r.h[i] = a.h[i] - b.h[i];
+    for (int i = 0; i < Jet<N, O, NG, G>::NH; ++i) r.h[i] = a.h[i] - b.h[i];
   }
   return r;
 }
-template <int N, int O>
-ILQC_HD Jet<N, O> operator-(const Jet<N, O>& a) {
-  Jet<N, O> r;
+template <int N, int O, int NG, int G>
+ILQC_HD Jet<N, O, NG, G> operator-(const Jet<N, O, NG, G>& a) {
+  Jet<N, O, NG, G> r;
   r.v = -a.v;
 #pragma unroll
   for (int i = 0; i < N; ++i) r.g[i] = -a.g[i];
   if constexpr (O >= 2) {
 #pragma unroll
-    for (int i = 0; i < Jet<N, O>::NH; ++i) r.h[i] = -a.h[i];
+    for (int i = 0; i < Jet<N, O, NG, G>::NH; ++i) r.h[i] = -a.h[i];
   }
   return r;
 }
-template <int N, int O> ILQC_HD Jet<N, O> operator+(const Jet<N, O>& a, double b) { Jet<N, O> r = a; r.v = a.v + b; return r; }
-template <int N, int O> ILQC_HD Jet<N, O> operator+(double b, const Jet<N, O>& a) { Jet<N, O> r = a; r.v = b + a.v; return r; }
-template <int N, int O> ILQC_HD Jet<N, O> operator-(const Jet<N, O>& a, double b) { Jet<N, O> r = a; r.v = a.v - b; return r; }
-template <int N, int O> ILQC_HD Jet<N, O> operator-(double b, const Jet<N, O>& a) { Jet<N, O> r = -a; r.v = b - a.v; return r; }
-template <int N, int O>
-ILQC_HD Jet<N, O> operator*(const Jet<N, O>& a, double b) {
-  Jet<N, O> r;
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> operator+(const Jet<N, O, NG, G>& a, double b) { Jet<N, O, NG, G> r = a; r.v = a.v + b; return r; }
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> operator+(double b, const Jet<N, O, NG, G>& a) { Jet<N, O, NG, G> r = a; r.v = b + a.v; return r; }
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> operator-(const Jet<N, O, NG, G>& a, double b) { Jet<N, O, NG, G> r = a; r.v = a.v - b; return r; }
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> operator-(double b, const Jet<N, O, NG, G>& a) { Jet<N, O, NG, G> r = -a; r.v = b - a.v; return r; }
+template <int N, int O, int NG, int G>
+ILQC_HD Jet<N, O, NG, G> operator*(const Jet<N, O, NG, G>& a, double b) {
+  Jet<N, O, NG, G> r;
   r.v = a.v * b;
 #pragma unroll
   for (int i = 0; i < N; ++i) r.g[i] = a.g[i] * b;
   if constexpr (O >= 2) {
 #pragma unroll
-    for (int i = 0; i < Jet<N, O>::NH; ++i) r.h[i] = a.h[i] * b;
+    for (int i = 0; i < Jet<N, O, NG, G>::NH; ++i) r.h[i] = a.h[i] * b;
   }
   return r;
 }
-template <int N, int O> ILQC_HD Jet<N, O> operator*(double b, const Jet<N, O>& a) { return a * b; }
-template <int N, int O>
-ILQC_HD Jet<N, O> operator/(const Jet<N, O>& a, double b) {
-  Jet<N, O> r;
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> operator*(double b, const Jet<N, O, NG, G>& a) { return a * b; }
+template <int N, int O, int NG, int G>
+ILQC_HD Jet<N, O, NG, G> operator/(const Jet<N, O, NG, G>& a, double b) {
+  Jet<N, O, NG, G> r;
   const double ib = 1.0 / b;
   r.v = a.v / b;
 #pragma unroll
   for (int i = 0; i < N; ++i) r.g[i] = a.g[i] * ib;
   if constexpr (O >= 2) {
 #pragma unroll
-    for (int i = 0; i < Jet<N, O>::NH; ++i) r.h[i] = a.h[i] * ib;
+    for (int i = 0; i < Jet<N, O, NG, G>::NH; ++i) r.h[i] = a.h[i] * ib;
   }
   return r;
 }
-template <int N, int O>
-ILQC_HD Jet<N, O> operator*(const Jet<N, O>& a, const Jet<N, O>& b) {
+template <int N, int O, int NG, int G>
+ILQC_HD Jet<N, O, NG, G> operator*(const Jet<N, O, NG, G>& a, const Jet<N, O, NG, G>& b) {
   return chain2(a, b, a.v * b.v, b.v, a.v, 0.0, 1.0, 0.0);
 }
-template <int N, int O>
-ILQC_HD Jet<N, O> operator/(const Jet<N, O>& a, const Jet<N, O>& b) {
+template <int N, int O, int NG, int G>
+ILQC_HD Jet<N, O, NG, G> operator/(const Jet<N, O, NG, G>& a, const Jet<N, O, NG, G>& b) {
   const double ib = 1.0 / b.v;
   const double q = a.v / b.v;
   // q = a/b : q_a = 1/b, q_b = -q/b, q_aa = 0, q_ab = -1/b^2, q_bb = 2q/b^2
   return chain2(a, b, q, ib, -q * ib, 0.0, -ib * ib, 2.0 * q * ib * ib);
 }
-template <int N, int O>
-ILQC_HD Jet<N, O> operator/(double a, const Jet<N, O>& b) {
+template <int N, int O, int NG, int G>
+ILQC_HD Jet<N, O, NG, G> operator/(double a, const Jet<N, O, NG, G>& b) {
   const double ib = 1.0 / b.v;
   const double q = a / b.v;
   return chain1(b, q, -q * ib, 2.0 * q * ib * ib);
@@ -202,54 +227,54 @@ ILQC_HD void jsincos(double a, double* s, double* c) {
 #endif
 }
 
-template <int N, int O> ILQC_HD Jet<N, O> jsin(const Jet<N, O>& a) {
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jsin(const Jet<N, O, NG, G>& a) {
   double s, c; jsincos(a.v, &s, &c);
   return chain1(a, s, c, -s);
 }
-template <int N, int O> ILQC_HD Jet<N, O> jcos(const Jet<N, O>& a) {
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jcos(const Jet<N, O, NG, G>& a) {
   double s, c; jsincos(a.v, &s, &c);
   return chain1(a, c, -s, -c);
 }
-template <int N, int O> ILQC_HD Jet<N, O> jtan(const Jet<N, O>& a) {
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jtan(const Jet<N, O, NG, G>& a) {
   const double t = ::tan(a.v);
   const double d = 1.0 + t * t;
   return chain1(a, t, d, 2.0 * t * d);
 }
-template <int N, int O> ILQC_HD Jet<N, O> jatan(const Jet<N, O>& a) {
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jatan(const Jet<N, O, NG, G>& a) {
   const double d = 1.0 / (1.0 + a.v * a.v);
   return chain1(a, ::atan(a.v), d, -2.0 * a.v * d * d);
 }
-template <int N, int O> ILQC_HD Jet<N, O> jatan2(const Jet<N, O>& y, const Jet<N, O>& x) {
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jatan2(const Jet<N, O, NG, G>& y, const Jet<N, O, NG, G>& x) {
   const double ir2 = 1.0 / (x.v * x.v + y.v * y.v);
   const double fy = x.v * ir2, fx = -y.v * ir2;
   const double fyy = -2.0 * x.v * y.v * ir2 * ir2;
   const double fxy = (y.v * y.v - x.v * x.v) * ir2 * ir2;
   return chain2(y, x, ::atan2(y.v, x.v), fy, fx, fyy, fxy, -fyy);
 }
-template <int N, int O> ILQC_HD Jet<N, O> jexp(const Jet<N, O>& a) {
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jexp(const Jet<N, O, NG, G>& a) {
   const double e = ::exp(a.v);
   return chain1(a, e, e, e);
 }
-template <int N, int O> ILQC_HD Jet<N, O> jlog(const Jet<N, O>& a) {
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jlog(const Jet<N, O, NG, G>& a) {
   const double i = 1.0 / a.v;
   return chain1(a, ::log(a.v), i, -i * i);
 }
-template <int N, int O> ILQC_HD Jet<N, O> jsqrt(const Jet<N, O>& a) {
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jsqrt(const Jet<N, O, NG, G>& a) {
   const double s = ::sqrt(a.v);
   const double d = 0.5 / s;
   return chain1(a, s, d, -0.5 * d / a.v);
 }
-template <int N, int O> ILQC_HD Jet<N, O> jsigmoid(const Jet<N, O>& a) {
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jsigmoid(const Jet<N, O, NG, G>& a) {
   const double s = 1.0 / (1.0 + ::exp(-a.v));
   const double d = s * (1.0 - s);
   return chain1(a, s, d, d * (1.0 - 2.0 * s));
 }
-template <int N, int O> ILQC_HD Jet<N, O> jsq(const Jet<N, O>& a) { return chain1(a, a.v * a.v, 2.0 * a.v, 2.0); }
-template <int N, int O> ILQC_HD Jet<N, O> jcube(const Jet<N, O>& a) {
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jsq(const Jet<N, O, NG, G>& a) { return chain1(a, a.v * a.v, 2.0 * a.v, 2.0); }
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jcube(const Jet<N, O, NG, G>& a) {
   return chain1(a, (a.v * a.v) * a.v, 3.0 * a.v * a.v, 6.0 * a.v);
 }
-template <int N, int O> ILQC_HD Jet<N, O> jmax0(const Jet<N, O>& a) {
-  return (a.v > 0.0) ? a : make_cst<Jet<N, O>>(0.0);
+template <int N, int O, int NG, int G> ILQC_HD Jet<N, O, NG, G> jmax0(const Jet<N, O, NG, G>& a) {
+  return (a.v > 0.0) ? a : make_cst<Jet<N, O, NG, G>>(0.0);
 }
 
 // ======================================================================================================

@@ -74,15 +74,22 @@ ILQC_GLOBAL_LB(ILQC_LB_ROLL) rollout_kernel(ilqc_model_desc m, int B, int n_thre
                         diffsq);
 }
 
-// one thread per (problem, time step); consecutive threads = consecutive problems of the same step
+// one thread per (problem, time step) and Hessian-entry group G; consecutive threads = consecutive problems
+// of the same step.  Groups: jets with more than 16 second-order components are split in 3 (28-double jets of
+// the bicycle model: 9.6 KB of spills per thread in one piece).
+#ifndef ILQC_HESS_GROUPS
+#define ILQC_HESS_GROUPS 3
+#endif
 template <class M>
+constexpr int kHessGroups = sym_size(M::NV) > 16 ? ILQC_HESS_GROUPS : 1;
+template <class M, int NG, int G>
 ILQC_GLOBAL_LB(ILQC_LB_BWD) hess_kernel(ilqc_model_desc m, int B, int n_probs, const int32_t* prob, const double* traj,
                                         const double* cmd, double* hess) {
   const long long i = (long long)blockIdx_x_times_blockDim() + ILQC_LOCAL_TID;
   if (i >= (long long)n_probs * m.horizon) return;
   const int a = (int)(i % n_probs), t = (int)(i / n_probs);
   const int b = prob ? prob[a] : a;
-  hess_body<M>(m, b, B, t, traj, cmd, hess);
+  hess_body<M, NG, G>(m, b, B, t, traj, cmd, hess);
 }
 
 template <class M>
@@ -248,7 +255,12 @@ template <>
 int Launch<ILQC_MODEL_INST>::hess(const ilqc_model_desc& m, int B, int n_probs, const int32_t* prob, const double* traj,
                                   const double* cmd, double* hess, stream_t st) {
   const long long n = (long long)n_probs * m.horizon;
-  ILQC_LAUNCH((hess_kernel<MI>), n, kBlock, st, m, B, n_probs, prob, traj, cmd, hess);
+  constexpr int NG = kHessGroups<MI>;
+  ILQC_LAUNCH((hess_kernel<MI, NG, 0>), n, kBlock, st, m, B, n_probs, prob, traj, cmd, hess);
+  if constexpr (NG > 1) ILQC_LAUNCH((hess_kernel<MI, NG, 1>), n, kBlock, st, m, B, n_probs, prob, traj, cmd, hess);
+  if constexpr (NG > 2) ILQC_LAUNCH((hess_kernel<MI, NG, 2>), n, kBlock, st, m, B, n_probs, prob, traj, cmd, hess);
+  if constexpr (NG > 3) ILQC_LAUNCH((hess_kernel<MI, NG, 3>), n, kBlock, st, m, B, n_probs, prob, traj, cmd, hess);
+  static_assert(NG <= 4, "at most 4 Hessian-entry groups");
   return ILQC_LAUNCH_OK();
 }
 

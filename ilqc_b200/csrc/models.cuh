@@ -136,7 +136,11 @@ ILQC_HD void integrate(int integ, double dt, F&& f, const S (&x)[N], S (&xn)[N])
 #ifndef ILQC_STAGE_UNROLL_JET1
 #define ILQC_STAGE_UNROLL_JET1 4
 #endif
-    constexpr int kStageUnroll = VAR ? 4 : ((is_jet<S>::value && sizeof(S) <= sizeof(double) * 16) ? ILQC_STAGE_UNROLL_JET1 : 1);
+#ifndef ILQC_STAGE_UNROLL_MAX_DOUBLES
+#define ILQC_STAGE_UNROLL_MAX_DOUBLES 16
+#endif
+    constexpr int kStageUnroll =
+        VAR ? 4 : ((is_jet<S>::value && sizeof(S) <= sizeof(double) * ILQC_STAGE_UNROLL_MAX_DOUBLES) ? ILQC_STAGE_UNROLL_JET1 : 1);
     S k[N], s[N], acc[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) s[i] = x[i];

@@ -580,7 +580,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
   // expansion and the metrics row 0 (run_min_algo.py:65-76)
   ILQC_PROF(PROF_FORWARD0, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(0, md, B, B, nullptr, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st))));
   ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
-  if (quad) ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, B, nullptr, w.traj, cmd, w.hess, st)));
+  if (quad) ILQC_PROF(PROF_LINEARIZE, 0, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, B, nullptr, w.traj, cmd, w.hess, st))));
   if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
   ILQC_LAUNCH((status_kernel), B, 256, st, P, B, 0, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
               n_done);
@@ -659,7 +659,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
 
     // re-expand at the accepted controls (algos_steps.py:376-378) and collect the metrics of this iteration
     ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
-  if (quad) ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, B, nullptr, w.traj, cmd, w.hess, st)));
+  if (quad) ILQC_PROF(PROF_LINEARIZE, 0, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, B, nullptr, w.traj, cmd, w.hess, st))));
     if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
     ILQC_LAUNCH((status_kernel), B, 256, st, P, B, it, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
                 n_done);
