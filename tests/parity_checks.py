@@ -188,3 +188,75 @@ def check_lq_synth(eng):
             # dense Newton cross-check of the reference test (it prints 8.5e-10 / 1.3e-11)
             assert relerr(diff[b, c], g[tag + "_newton_diff"]) < 1e-8
             assert abs(float(jcst[b, c]) - float(g[tag + "_newton_opt"])) < 1e-8 * abs(float(g[tag + "_newton_opt"]))
+
+
+# ---- randomised configurations against the oracle (beyond the golden vectors) ---------------------------
+def random_env_cfg(seed):
+    """A random but valid environment configuration: every constructor argument the models take is drawn
+    (integrator, cost, time penalty, track, weights, dt, horizon offsets, barrier weights, physical times)."""
+    r = np.random.default_rng(seed)
+    kind = ["pendulum", "cart_pendulum", "simple_car", "real_car"][seed % 4]
+    u = lambda lo, hi: float(r.uniform(lo, hi))
+    if kind == "pendulum":
+        return dict(env="pendulum", horizon=4, dt=u(0.01, 0.06), reg_speed=u(0.05, 0.5), reg_ctrl=u(1e-6, 1e-2),
+                    stay_put_time=[None, 0.05][int(r.integers(2))])
+    if kind == "cart_pendulum":
+        return dict(env="cart_pendulum", horizon=4, dt=u(0.02, 0.06), reg_speed=u(0.05, 0.5), reg_ctrl=u(1e-6, 1e-2),
+                    reg_barrier=u(0.5, 5.0), stay_put_time=u(0.03, 0.12), x_limits=[None, (-0.4, 0.4)][int(r.integers(2))],
+                    discretization=["euler", "rk4cst", "rk4"][int(r.integers(3))])
+    cfg = dict(env=kind, horizon=3, dt=u(0.01, 0.05), track=["simple", "complex", "circle", "line", "bend"][int(r.integers(5))],
+               discretization=["euler", "rk4_cst_ctrl", "rk4"][int(r.integers(3))], cost=["contouring", "exact"][int(r.integers(4) == 0)],
+               time_penalty=["vref_squared", "tref", "dref", "dref_squared"][int(r.integers(4))],
+               reg_cont=u(0.05, 5.0), reg_lag=u(0.5, 20.0), reg_speed=u(0.05, 2.0), reg_bar=u(0.0, 200.0), vref=u(1.0, 3.5),
+               vinit=u(0.6, 2.0), reg_ctrl=[u(1e-6, 1e-3), (u(1e-6, 1e-3), u(1e-6, 1e-3))][int(r.integers(2))])
+    if int(r.integers(3)) == 0:
+        cfg["reg_obs"] = u(0.5, 50.0)
+    return cfg
+
+
+def check_random_config_vs_oracle(eng, seed, tol=1e-9):
+    """Expansion (first and second order), backward passes (linquad / Newton / DDP) and both roll-outs of a random
+    configuration at a random state and controls: engine vs the oracle's autograd (oracle/ilqc_oracle.py)."""
+    from oracle import ilqc_oracle as orc
+    cfg = random_env_cfg(seed)
+    env, oenv = make_env(cfg), orc.make_env(cfg)
+    r = np.random.default_rng(1000 + seed)
+    nx, nu, H = env.dim_state, env.dim_ctrl, env.horizon
+    x0 = oenv.init_state.detach().clone()
+    assert relerr(env.init_state, x0.numpy()) < 1e-14
+    x0 = x0 + torch.tensor(0.05 * r.normal(size=nx))
+    if cfg["env"] in ("simple_car", "real_car"):
+        x0[-1] = abs(float(x0[-1])) + 0.3          # vtref > 0 (log barrier)
+        x0[-2] = abs(float(x0[-2])) + float(r.uniform(0.0, 3.0))   # somewhere along the track
+    cmd = torch.tensor(0.3 * r.normal(size=(H, nu)))
+    oenv.init_state = x0.clone()
+    traj, costs, steps = orc.forward(oenv, cmd.clone().requires_grad_(True), approx="quad")
+    lam = torch.tensor(r.normal(size=(H, nx)))
+    ex = eng.expand_dense(env, x0.reshape(1, -1), cmd.unsqueeze(0), lam=lam.unsqueeze(0))
+    tr, ct, tot = eng.rollout_cost(env, x0.reshape(1, -1), cmd.unsqueeze(0))
+    errs = dict(traj=relerr(tr[0], torch.stack(traj).detach().numpy()),
+                total=abs(float(tot[0]) - float(sum(costs))) / (abs(float(sum(costs))) + 1e-300))
+    for t, st in enumerate(steps):
+        hxx, huu, hxu = orc.hess_dyn(st, lam[t], nx, nu)
+        for key, a, b in (("A", ex["A"][0, t], st.A), ("B", ex["B"][0, t], st.B), ("p", ex["p"][0, t + 1], st.p),
+                          ("P", ex["P"][0, t + 1], st.P), ("q", ex["q"][0, t], st.q.reshape(nu)),
+                          ("Q", ex["Q"][0, t], st.Q.reshape(nu, nu)), ("Huu", ex["Huu"][0, t], huu), ("Hxu", ex["Hxu"][0, t], hxu)):
+            errs[f"{key}{t}"] = float((a.cpu() - b.detach()).abs().max() / (b.detach().abs().max() + 1e-12))
+        if t > 0:
+            errs[f"Hxx{t}"] = float((ex["Hxx"][0, t].cpu() - hxx.detach()).abs().max() / (hxx.detach().abs().max() + 1e-12))
+    lin = eng.linearize(env, x0.reshape(1, -1), cmd.unsqueeze(0))
+    one = lambda v: torch.tensor([[v]], dtype=torch.float64)
+    for mode, mid in (("linquad", _lib.BWD_LINQUAD), ("newton", _lib.BWD_QUAD_NEWTON), ("ddp", _lib.BWD_QUAD_DDP)):
+        reg = 0.7
+        gains, jcst, feas = orc.backward(steps, reg, mode=mode)
+        bw = eng.backward(lin, mid, one(reg))
+        errs[mode + "_K"] = relerr(bw["K"][0, 0], torch.stack([K for K, _ in gains]).detach().numpy())
+        errs[mode + "_k"] = relerr(bw["k"][0, 0], torch.stack([k for _, k in gains]).detach().numpy())
+        errs[mode + "_jcst"] = abs(float(bw["jcst"][0, 0]) - float(jcst)) / (abs(float(jcst)) + 1e-300)
+        d, _, _ = eng.rollout(lin, _lib.ROLL_LIN, one(0.6), bw)
+        errs[mode + "_rol"] = relerr(d[0, 0], orc.roll_out_lin(steps, gains, 0.6).detach().numpy())
+        d, _, _ = eng.rollout(lin, _lib.ROLL_EXACT, one(0.6), bw)
+        errs[mode + "_roe"] = relerr(d[0, 0], orc.roll_out_exact(oenv, traj, gains, cmd, 0.6).detach().numpy())
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, (seed, cfg, bad)
+    return errs

@@ -259,3 +259,9 @@ def test_config5_mpc_concurrent_episodes(cuda_engine):
     rs = run_mpc_batched(env, full_horizon=42, window_size=40, overlap=39, max_iter=10, x0=x0[idx], weights=w[idx],
                          engine=cuda_engine)
     assert torch.equal(rs.cmd, r.cmd[idx.to(r.cmd.device)])
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_config_vs_oracle(cuda_engine, seed):
+    """16 random environment configurations (4 per model family) against the oracle's autograd."""
+    pc.check_random_config_vs_oracle(cuda_engine, seed)

@@ -39,3 +39,9 @@ def test_run_free(sim_engine, name):
 
 def test_lq_synth_dense_riccati_vs_dense_newton(sim_engine):
     pc.check_lq_synth(sim_engine)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_config_vs_oracle(sim_engine, seed):
+    """16 random environment configurations (4 per model family) against the oracle's autograd."""
+    pc.check_random_config_vs_oracle(sim_engine, seed)
