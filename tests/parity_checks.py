@@ -257,6 +257,16 @@ def check_random_config_vs_oracle(eng, seed, tol=1e-9):
         errs[mode + "_rol"] = relerr(d[0, 0], orc.roll_out_lin(steps, gains, 0.6).detach().numpy())
         d, _, _ = eng.rollout(lin, _lib.ROLL_EXACT, one(0.6), bw)
         errs[mode + "_roe"] = relerr(d[0, 0], orc.roll_out_exact(oenv, traj, gains, cmd, 0.6).detach().numpy())
+    # two solver iterations from these controls with a second- and a first-order algorithm (the solver contracts the
+    # stored dynamics-Hessian tensor, eng.backward above recomputes it: both paths are compared with the oracle)
+    for algo in (["ddp_quad_reg", "classic_quad_reg"][seed % 2], ["ddp_linquad_reg", "classic_linquad_dir"][(seed // 2) % 2]):
+        oenv.init_state = x0.clone()
+        ocmd, _, m = orc.run_min_algo(oenv, max_iter=2, algo=algo, prev_cmd=cmd.clone())
+        res = eng.solve(env, algo, 2, x0=x0.reshape(1, -1), cmd0=cmd.unsqueeze(0))
+        n = min(len(m["cost"]), int(res.n_done[0]) + 1)
+        errs[algo + "_cost"] = relerr(res.cost[0, :n], np.array(m["cost"][:n]))
+        if ocmd is not None and n == 3:
+            errs[algo + "_cmd"] = relerr(res.cmd[0], ocmd.detach().numpy())
     bad = {k: v for k, v in errs.items() if not v < tol}
     assert not bad, (seed, cfg, bad)
     return errs
