@@ -280,15 +280,21 @@ def run_ours(args):
     value = tot_its.item() / elapsed_s
 
     # ---- end-to-end through the C ABI with HOST buffers (copies inside the timed region) ----
+    # every step copies its inputs (initial states, per-problem cost weights, step sizes) from pinned host memory and
+    # reads its results (controls, metrics, status) back; the initial controls are zeros = run_min_algo(prev_cmd=None),
+    # created on the device like the reference creates them itself (run_min_algo.py:57)
     x0h = x0.clone().pin_memory()
-    cmdh = torch.zeros(B, 100, NU, dtype=torch.float64).pin_memory()
+    wh = w.clone().pin_memory()
+    wd_e2e = torch.empty_like(wd)
+    cmdh = torch.empty(B, 100, NU, dtype=torch.float64).pin_memory()
     steph = torch.empty(B, dtype=torch.float64).pin_memory()
     e2e_steps = max(1, min(args.steps, 5))
 
     def e2e_step():
-        cmdh.zero_()
         steph.fill_(100.0)
-        return eng.solve_host(env, ALGO, iters, x0h, cmdh, steph, weights=wd, n_candidates=L, scheduler=args.scheduler)
+        wd_e2e.copy_(wh, non_blocking=True)
+        return eng.solve_host(env, ALGO, iters, x0h, cmdh, steph, weights=wd_e2e, n_candidates=L, scheduler=args.scheduler,
+                              cmd0_host=None)
 
     e2e_step()
     barrier()
@@ -303,7 +309,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_tot, op=dist.ReduceOp.SUM)
-    h2d = 8 * (B * NX + B * 100 * NU + B)
+    h2d = 8 * (B * NX + 3 * B + B)
     d2h = 8 * (B * 100 * NU + B + 3 * B * (iters + 1)) + 8 * B
 
     if rank != 0:

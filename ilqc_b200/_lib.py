@@ -72,7 +72,7 @@ PROTOTYPES = {
     "ilqc_solve_workspace_bytes": (C.c_size_t, [_MP, _AP, C.c_int]),
     "ilqc_solve": (C.c_int, [_MP, _AP, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "ilqc_solve_host_workspace_bytes": (C.c_size_t, [_MP, _AP, C.c_int, C.c_int]),
-    "ilqc_solve_host": (C.c_int, [_MP, _AP, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "ilqc_solve_host": (C.c_int, [_MP, _AP, C.c_int, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "ilqc_to_soa": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
     "ilqc_from_soa": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
     "ilqc_profile_enable": (C.c_int, [C.c_int]),

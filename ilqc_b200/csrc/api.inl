@@ -232,8 +232,8 @@ size_t ilqc_solve_host_workspace_bytes(const ilqc_model_desc* m, const ilqc_algo
   const size_t ws = ilqc_solve_workspace_bytes(m, a, B);
   return ws + align_up(host_stage_doubles(d, m->horizon, B, n_iter) * sizeof(double)) + align_up((size_t)2 * B * 4) + 512;
 }
-int ilqc_solve_host(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const double* x0_host, double* cmd_host,
-                    double* stepsize_host, int n_iter, double* cost_host, double* gnorm_host, double* step_rep_host,
+int ilqc_solve_host(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const double* x0_host,
+                    const double* cmd0_host, double* cmd_host, double* stepsize_host, int n_iter, double* cost_host, double* gnorm_host, double* step_rep_host,
                     int32_t* n_done_host, int32_t* status_host, void* workspace, size_t workspace_bytes,
                     void* stream) {
   Dims d;
@@ -258,10 +258,14 @@ int ilqc_solve_host(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, co
   int32_t* status_d = ints + B;
 #define ILQC_CHECK(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
   ILQC_CHECK(dev_h2d(x0_aos, x0_host, sizeof(double) * B * d.nx, st));
-  ILQC_CHECK(dev_h2d(cmd_aos, cmd_host, sizeof(double) * B * H * d.nu, st));
   ILQC_CHECK(dev_h2d(step_d, stepsize_host, sizeof(double) * B, st));
   ILQC_CHECK(ilqc_to_soa(x0_aos, x0_soa, B, d.nx, stream));
-  ILQC_CHECK(ilqc_to_soa(cmd_aos, cmd_soa, B, H * d.nu, stream));
+  if (cmd0_host) {
+    ILQC_CHECK(dev_h2d(cmd_aos, cmd0_host, sizeof(double) * B * H * d.nu, st));
+    ILQC_CHECK(ilqc_to_soa(cmd_aos, cmd_soa, B, H * d.nu, stream));
+  } else {
+    ILQC_CHECK(dev_memset(cmd_soa, 0, sizeof(double) * B * H * d.nu, st));  // prev_cmd=None: zeros (run_min_algo.py:57)
+  }
   ILQC_CHECK(solve_dispatch(m, a, B, x0_soa, cmd_soa, step_d, n_iter, met_soa, met_soa + mrows, met_soa + 2 * mrows,
                             n_done_d, status_d, nullptr, workspace, ws, st));
   ILQC_CHECK(ilqc_from_soa(cmd_soa, cmd_aos, B, H * d.nu, stream));

@@ -327,8 +327,12 @@ class Engine:
                            ls_trips=trips[:max_iter].t().contiguous() if record_trips else None)
 
     def solve_host(self, env, algo, max_iter, x0_host, cmd_host, stepsize_host, weights=None, t0=None,
-                   n_candidates=128, compute_grad_norm=True, scheduler=0):
-        """Same solve through ilqc_solve_host: HOST (pinned) tensors in the reference layout, copies inside."""
+                   n_candidates=128, compute_grad_norm=True, scheduler=0, cmd0_host="same"):
+        """Same solve through ilqc_solve_host: HOST (pinned) tensors in the reference layout, copies inside.
+        cmd_host [B,H,nu] receives the controls; cmd0_host = initial controls ("same": cmd_host in place,
+        None: zeros like run_min_algo(prev_cmd=None), nothing is copied to the device for them)."""
+        if isinstance(cmd0_host, str):
+            cmd0_host = cmd_host
         B, H, nu = cmd_host.shape
         d, keep = self.make_desc(env, H, B, t0, weights)
         a = self.algo_desc(algo, n_candidates, True, compute_grad_norm, 0, scheduler)
@@ -341,8 +345,8 @@ class Engine:
         status = torch.empty(B, dtype=torch.int32, pin_memory=pin)
         nbytes = self.lib.ilqc_solve_host_workspace_bytes(C.byref(d), C.byref(a), B, max_iter)
         ws = self.workspace(nbytes)
-        _lib.check(self.lib.ilqc_solve_host(C.byref(d), C.byref(a), B, self._ptr(x0_host), self._ptr(cmd_host),
-                                            self._ptr(stepsize_host), max_iter, self._ptr(cost), self._ptr(gnorm),
+        _lib.check(self.lib.ilqc_solve_host(C.byref(d), C.byref(a), B, self._ptr(x0_host), self._ptr(cmd0_host),
+                                            self._ptr(cmd_host), self._ptr(stepsize_host), max_iter, self._ptr(cost), self._ptr(gnorm),
                                             self._ptr(srep), self._ptr(n_done), self._ptr(status), self._ptr(ws),
                                             C.c_size_t(nbytes), self._stream()), "ilqc_solve_host")
         return SolveResult(cmd=cmd_host, stepsize=stepsize_host, cost=cost, norm_grad_obj=gnorm,

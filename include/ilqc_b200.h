@@ -176,11 +176,13 @@ int ilqc_solve(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const d
                double* stepsize, int n_iter, double* cost, double* gnorm, double* step_rep, int32_t* n_done,
                int32_t* status, int32_t* ls_trips, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Same call for HOST buffers in the reference's own layout (x0_host [B][nx], cmd_host [B][H][nu],
+/* Same call for HOST buffers in the reference's own layout (x0_host [B][nx], cmd [B][H][nu],
  * stepsize_host [B], metrics [B][n_iter+1]): copies in, transposes on the device, solves, copies back.
+ * cmd0_host: initial controls, or NULL to start from zeros like run_min_algo(prev_cmd=None)
+ * (run_min_algo.py:53-57; nothing is copied in then); cmd_host: output (may alias cmd0_host).
  * The desc pointers (spline tables, per-problem arrays) are still device pointers. */
 int ilqc_solve_host(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const double* x0_host,
-                    double* cmd_host, double* stepsize_host, int n_iter, double* cost_host,
+                    const double* cmd0_host, double* cmd_host, double* stepsize_host, int n_iter, double* cost_host,
                     double* gnorm_host, double* step_rep_host, int32_t* n_done_host, int32_t* status_host,
                     void* workspace, size_t workspace_bytes, void* stream);
 size_t ilqc_solve_host_workspace_bytes(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, int n_iter);

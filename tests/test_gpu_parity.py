@@ -154,6 +154,11 @@ def test_solve_host_matches_device_path(cuda_engine):
     steph = torch.full((256,), 100.0, dtype=torch.float64).pin_memory()
     rh = cuda_engine.solve_host(env, "ddp_linquad_reg", 2, x0h, cmdh, steph, weights=w)
     assert torch.equal(rh.cost, r.cost.cpu()) and torch.equal(cmdh, r.cmd.cpu()) and torch.equal(steph, r.stepsize.cpu())
+    # cmd0_host = NULL: zeros created on the device (run_min_algo(prev_cmd=None)), separate output buffer
+    out = torch.full((256, 25, 3), 7.0, dtype=torch.float64).pin_memory()
+    steph.fill_(100.0)
+    rz = cuda_engine.solve_host(env, "ddp_linquad_reg", 2, x0h, out, steph, weights=w, cmd0_host=None)
+    assert torch.equal(rz.cost, r.cost.cpu()) and torch.equal(out, r.cmd.cpu())
 
 
 def test_lq_synth_dense_riccati_vs_dense_newton(cuda_engine):
