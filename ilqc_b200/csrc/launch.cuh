@@ -21,7 +21,7 @@ inline long long& launch_counter() { static long long n = 0; return n; }
 #define ILQC_GLOBAL_LB(minblocks) static void
 #define ILQC_TID (::ilqc::g_sim_tid)
 #define ILQC_LOCAL_TID (::ilqc::g_sim_tid)
-#define blockIdx_x_times_blockDim() 0
+#define ILQC_BLOCK_BASE 0
 #define ILQC_UNPAREN(...) __VA_ARGS__
 #define ILQC_LAUNCH(kern, n, block, stream, ...)                 \
   do {                                                           \
@@ -43,7 +43,7 @@ inline long long& launch_counter() { static long long n = 0; return n; }
 #define ILQC_GLOBAL_LB(minblocks) __global__ void __launch_bounds__(ILQC_BLOCK, minblocks)
 #define ILQC_TID ((int)(blockIdx.x * blockDim.x + threadIdx.x))
 #define ILQC_LOCAL_TID ((long long)threadIdx.x)
-#define blockIdx_x_times_blockDim() ((long long)blockIdx.x * blockDim.x)
+#define ILQC_BLOCK_BASE ((long long)blockIdx.x * blockDim.x)
 #define ILQC_UNPAREN(...) __VA_ARGS__
 #define ILQC_LAUNCH(kern, n, block, stream, ...)                                                   \
   do {                                                                                             \

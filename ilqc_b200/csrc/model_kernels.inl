@@ -85,7 +85,7 @@ constexpr int kHessGroups = sym_size(M::NV) > 16 ? ILQC_HESS_GROUPS : 1;
 template <class M, int NG, int G>
 ILQC_GLOBAL_LB(ILQC_LB_BWD) hess_kernel(ilqc_model_desc m, int B, int n_probs, const int32_t* prob, const double* traj,
                                         const double* cmd, double* hess) {
-  const long long i = (long long)blockIdx_x_times_blockDim() + ILQC_LOCAL_TID;
+  const long long i = (long long)ILQC_BLOCK_BASE + ILQC_LOCAL_TID;
   if (i >= (long long)n_probs * m.horizon) return;
   const int a = (int)(i % n_probs), t = (int)(i / n_probs);
   const int b = prob ? prob[a] : a;
