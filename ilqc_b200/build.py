@@ -109,7 +109,8 @@ def build_hostsim(verbose=True, force=False):
 
 
 if __name__ == "__main__":
-    what = sys.argv[1] if len(sys.argv) > 1 else "cuda"
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    what = args[0] if args else "cuda"
     if what in ("cuda", "all"):
         build_cuda(force="--force" in sys.argv)
     if what in ("hostsim", "all"):
