@@ -270,3 +270,42 @@ def check_random_config_vs_oracle(eng, seed, tol=1e-9):
     bad = {k: v for k, v in errs.items() if not v < tol}
     assert not bad, (seed, cfg, bad)
     return errs
+
+
+# ---- dense cross-check at batch scale (the idea of the reference's tests/test_auto_lin_quad.py, tests/utils.py) -------
+def check_riccati_vs_dense_newton(eng, B=48, H=10, reg=0.3):
+    """lin_quad_backward + roll_out_lin is the Newton step of the linear-quadratic model.  For a batch of random
+    bicycle problems the step from the Riccati kernels is compared with a dense solve of the same model assembled
+    in torch from the dense expansion: dx = G v (block lower-triangular from A_t, B_t), Hessian (Q + reg) + G^T P G,
+    gradient q + G^T p, v* = -Hess^{-1} grad."""
+    env = make_env(dict(env="real_car", track="simple", cost="contouring", discretization="rk4_cst_ctrl", horizon=H, dt=0.02))
+    g = torch.Generator().manual_seed(7)
+    nx, nu = env.dim_state, env.dim_ctrl
+    x0 = env.init_state.reshape(1, -1).repeat(B, 1)
+    x0[:, 3] = 1.0 + 0.05 * torch.randn(B, generator=g, dtype=torch.float64)
+    x0[:, 7] = x0[:, 3]
+    cmd = 0.2 * torch.randn(B, H, nu, generator=g, dtype=torch.float64)
+    ex = eng.expand_dense(env, x0, cmd)
+    A, Bm, p, P, q, Q = (ex[k].cpu() for k in ("A", "B", "p", "P", "q", "Q"))
+    n = H * nu
+    G = torch.zeros(B, H + 1, nx, n, dtype=torch.float64)      # dx_t = G[t] v
+    for t in range(H):
+        G[:, t + 1] = A[:, t] @ G[:, t]
+        G[:, t + 1, :, t * nu:(t + 1) * nu] += Bm[:, t]
+    Hess = torch.zeros(B, n, n, dtype=torch.float64)
+    grad = q.reshape(B, n).clone()
+    for t in range(H):
+        Hess[:, t * nu:(t + 1) * nu, t * nu:(t + 1) * nu] += Q[:, t] + reg * torch.eye(nu, dtype=torch.float64)
+    for t in range(1, H + 1):
+        Hess += G[:, t].transpose(1, 2) @ P[:, t] @ G[:, t]
+        grad += (G[:, t].transpose(1, 2) @ p[:, t].unsqueeze(-1)).squeeze(-1)
+    v_dense = -torch.linalg.solve(Hess, grad.unsqueeze(-1)).squeeze(-1).reshape(B, H, nu)
+    lin = eng.linearize(env, x0, cmd)
+    bw = eng.backward(lin, _lib.BWD_LINQUAD, torch.full((B, 1), reg, dtype=torch.float64))
+    d, _, _ = eng.rollout(lin, _lib.ROLL_LIN, torch.ones(B, 1, dtype=torch.float64), bw)
+    err = relerr(d[:, 0], v_dense.numpy())
+    # model decrease: jcst = 1/2 grad . v*
+    dec = 0.5 * (grad * v_dense.reshape(B, n)).sum(1)
+    err_j = relerr(bw["jcst"][:, 0], dec.numpy())
+    assert err < 1e-8 and err_j < 1e-8, (err, err_j)
+    return err, err_j

@@ -270,3 +270,8 @@ def test_config5_mpc_concurrent_episodes(cuda_engine):
 def test_random_config_vs_oracle(cuda_engine, seed):
     """16 random environment configurations (4 per model family) against the oracle's autograd."""
     pc.check_random_config_vs_oracle(cuda_engine, seed)
+
+
+def test_riccati_vs_dense_newton_batch(cuda_engine):
+    """Dense cross-check (the idea of the reference's tests/test_auto_lin_quad.py) on a batch of bicycle problems."""
+    pc.check_riccati_vs_dense_newton(cuda_engine, B=256)

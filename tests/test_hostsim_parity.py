@@ -45,3 +45,7 @@ def test_lq_synth_dense_riccati_vs_dense_newton(sim_engine):
 def test_random_config_vs_oracle(sim_engine, seed):
     """16 random environment configurations (4 per model family) against the oracle's autograd."""
     pc.check_random_config_vs_oracle(sim_engine, seed)
+
+
+def test_riccati_vs_dense_newton_batch(sim_engine):
+    pc.check_riccati_vs_dense_newton(sim_engine)
