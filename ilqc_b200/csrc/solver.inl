@@ -492,22 +492,34 @@ inline bool trace_rounds() {
 // what lies beyond the accepted trip.  Policy from the trip statistics of the bicycle workload (trips 3-5 for
 // 92 % of the problems once the iterates settle, a 0.2 % tail of 30-110 trips) and the measured launch costs
 // (tools/sim_round_policy.py, profiles/r01_round_policy.txt):
-//   round 0: up to 4 candidates within 1.75 waves   (most problems need the first 3-4 steps 8s, 4s, 2s, s)
+//   round 0: clamp(49152 / n_active, 4, 16) candidates within 1.75 waves: 4 for a full batch (most problems
+//            need the first 3-4 steps 8s, 4s, 2s, s); small batches leave the GPU idle, their launches are
+//            latency-bound (the cost of a launch is flat below ~20 k slots), so a wider first round is free and
+//            saves whole rounds (simulated -28 % at 4096 problems, -50 % at <= 1024)
 //   round 1: up to 3 within one wave                (trip 5-7)
 //   round 2: up to 16 within one wave
-//   later  : up to 128 within one wave              (stragglers: finish the 30-110 halvings in one launch)
+//   later, or as soon as <= 148 problems are left: up to 128 within one wave (stragglers: finish the 30-110
+//            halvings in one launch)
 // round < 0 (asynchronous scheduler, no round structure): one wave, Lmax.
 inline size_t round_capacity(int round) {
   const size_t wave = (size_t)wave_slots();
   return round == 0 ? wave + (3 * wave) / 4 : wave;
 }
 inline int round_candidates(int round, int n_active, int Lmax) {
-  static const int cap_l[4] = {4, 3, 16, 128};
+  const int n = n_active > 0 ? n_active : 1;
   if (round >= 0) {
-    const int c = cap_l[round < 3 ? round : 3];
+    int c;
+    if (round == 0) {
+      c = 49152 / n;
+      c = c < 4 ? 4 : (c > 16 ? 16 : c);
+    } else if (n <= 148 || round >= 3) {
+      c = 128;
+    } else {
+      c = round == 1 ? 3 : 16;
+    }
     if (c < Lmax) Lmax = c;
   }
-  int L = (int)(round_capacity(round) / (size_t)(n_active > 0 ? n_active : 1));
+  int L = (int)(round_capacity(round) / (size_t)n);
   return L < 1 ? 1 : (L > Lmax ? Lmax : L);
 }
 // slots the workspace must hold: n_active * round_candidates(...) <= max(B, largest round capacity)
