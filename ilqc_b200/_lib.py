@@ -50,7 +50,7 @@ class ModelDesc(C.Structure):
 class AlgoDesc(C.Structure):
     """struct ilqc_algo_desc (include/ilqc_b200.h)."""
     _fields_ = [(n, _i) for n in ("algo_type", "approx", "step_mode", "n_candidates", "line_search",
-                                  "max_ls_trips", "compute_grad_norm", "scheduler", "handle_bad_dir")]
+                                  "max_ls_trips", "compute_grad_norm", "scheduler", "handle_bad_dir", "expansion")]
 
 
 _MP, _AP = C.POINTER(ModelDesc), C.POINTER(AlgoDesc)

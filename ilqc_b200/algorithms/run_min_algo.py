@@ -47,7 +47,7 @@ def check_cvg_status(metrics: dict, verbose: bool = True) -> str:
 def run_min_algo_batched(env, max_iter: int = 10, algo: str = "ddp_linquad_reg", stepsize=None,
                          line_search: bool = True, handle_bad_dir: str = "check_total_value", x0=None,
                          prev_cmd=None, weights=None, t0=None, batch=None, n_candidates: int = 128,
-                         compute_grad_norm: bool = True, engine=None):
+                         compute_grad_norm: bool = True, engine=None, expansion: int = 0):
     """B problems at once.  x0 [B,nx], prev_cmd [B,H,nu] (None: zeros), stepsize float or [B], weights [B,3]
     (Car reg_cont/reg_lag/reg_speed), t0 int or [B] (init_time_iter).  Returns ilqc_b200.engine.SolveResult
     with device tensors: cmd [B,H,nu], stepsize [B], cost / norm_grad_obj / stepsize_reported [B,max_iter+1],
@@ -58,7 +58,8 @@ def run_min_algo_batched(env, max_iter: int = 10, algo: str = "ddp_linquad_reg",
     eng = engine or default_engine()
     return eng.solve(env, algo, max_iter, x0=x0, cmd0=prev_cmd, stepsize=stepsize, batch=batch, weights=weights,
                      t0=env.init_time_iter if t0 is None else t0, n_candidates=n_candidates,
-                     line_search=line_search, compute_grad_norm=compute_grad_norm, handle_bad_dir=handle_bad_dir)
+                     line_search=line_search, compute_grad_norm=compute_grad_norm, handle_bad_dir=handle_bad_dir,
+                     expansion=expansion)
 
 
 def run_min_algo(env, max_iter: int = 10, algo: str = "ddp_linquad_reg", stepsize: Optional[float] = None,

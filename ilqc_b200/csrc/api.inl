@@ -173,7 +173,7 @@ size_t ilqc_solve_workspace_bytes(const ilqc_model_desc* m, const ilqc_algo_desc
   Dims d;
   if (get_dims(m, &d) || !a || B <= 0 || a->n_candidates < 1) return 0;
   Workspace w;
-  carve(&w, nullptr, d, m->horizon, B, a->n_candidates, needs_hess(a));
+  carve(&w, nullptr, d, m->horizon, B, a->n_candidates, needs_hess(a), a->expansion == 1);
   return w.bytes;
 }
 

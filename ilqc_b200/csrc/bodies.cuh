@@ -134,6 +134,32 @@ ILQC_HD void forward_body(const ilqc_model_desc& m, int b, int B, const double* 
 }
 
 // ----------------------------------------------------------------------------------------------------
+// time-parallel expansion (ilqc_algo_desc.expansion = 1): one thread per (problem, time step) expands step t
+// from the stored trajectory; gsq[t][b] = |grad_ctrl|^2 + |grad_state|^2 of the step (summed in time order by
+// cnorm_body, like the sequential kernel does)
+// ----------------------------------------------------------------------------------------------------
+template <class M>
+ILQC_HD void expand_body(const ilqc_model_desc& m, int b, int B, int t, const double* __restrict__ traj,
+                         const double* __restrict__ cmd, double* __restrict__ lin, double* __restrict__ gsq) {
+  constexpr int NX = M::NX, NU = M::NU;
+  const Weights w = load_weights(m, b, B);
+  const int t0 = load_t0(m, b);
+  double x[NX], u[NU], xn[NX], c, g;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = traj[((size_t)t * NX + i) * B + b];
+#pragma unroll
+  for (int k = 0; k < NU; ++k) u[k] = cmd[((size_t)t * NU + k) * B + b];
+  double* rec = lin + (size_t)t * Layout<M>::stride * B + b;
+  expand_step<M>(m, w, x, u, t0 + t + 1, xn, &c, &g, [&](int slot, double v) { rec[(size_t)slot * B] = v; });
+  gsq[(size_t)t * B + b] = g;
+}
+ILQC_HD void cnorm_body(int b, int B, int H, const double* __restrict__ gsq, double* __restrict__ cnorm) {
+  double s = 0.0;
+  for (int t = 0; t < H; ++t) s += gsq[(size_t)t * B + b];
+  cnorm[b] = ::sqrt(s);
+}
+
+// ----------------------------------------------------------------------------------------------------
 // loads of the packed record into the Riccati operands.  `rd(slot)` returns entry `slot` of the record.
 // ----------------------------------------------------------------------------------------------------
 struct GlobalRec {  // record in HBM: [component][problem], this thread's problem

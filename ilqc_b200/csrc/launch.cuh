@@ -103,6 +103,9 @@ struct Launch {
   static int forward(int order, const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob,
                      const double* x0, const double* cmd, double* lin, double* traj, double* cost_t, double* total,
                      double* cnorm, stream_t st);
+  // time-parallel expansion (ilqc_algo_desc.expansion = 1): gsq = scratch [H][B]
+  static int expand_parallel(const ilqc_model_desc& m, int B, int n_probs, const int32_t* prob, const double* x0,
+                             const double* cmd, double* lin, double* traj, double* gsq, double* cnorm, stream_t st);
   static int expand_dense(const ilqc_model_desc& m, int B, const double* x0, const double* cmd, int order,
                           double* A, double* Bm, double* p, double* P, double* q, double* Q, const double* lam,
                           double* Hxx, double* Hxu, double* Huu, stream_t st);

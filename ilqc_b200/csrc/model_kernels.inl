@@ -74,6 +74,21 @@ ILQC_GLOBAL_LB(ILQC_LB_ROLL) rollout_kernel(ilqc_model_desc m, int B, int n_thre
                         diffsq);
 }
 
+template <class M>
+ILQC_GLOBAL_LB(ILQC_LB_FWD1) expand_kernel(ilqc_model_desc m, int B, int n_probs, const int32_t* prob, const double* traj,
+                                           const double* cmd, double* lin, double* gsq) {
+  const long long i = (long long)ILQC_BLOCK_BASE + ILQC_LOCAL_TID;
+  if (i >= (long long)n_probs * m.horizon) return;
+  const int a = (int)(i % n_probs), t = (int)(i / n_probs);
+  expand_body<M>(m, prob ? prob[a] : a, B, t, traj, cmd, lin, gsq);
+}
+template <class M>
+ILQC_GLOBAL cnorm_kernel(ilqc_model_desc m, int B, int n_probs, const int32_t* prob, const double* gsq, double* cnorm) {
+  const int a = ILQC_TID;
+  if (a >= n_probs) return;
+  cnorm_body(prob ? prob[a] : a, B, m.horizon, gsq, cnorm);
+}
+
 // one thread per (problem, time step) and Hessian-entry group G; consecutive threads = consecutive problems
 // of the same step.  Groups: jets with more than 16 second-order components are split in 3 (28-double jets of
 // the bicycle model: 9.6 KB of spills per thread in one piece).
@@ -208,6 +223,18 @@ int Launch<ILQC_MODEL_INST>::forward(int order, const ilqc_model_desc& m, int B,
     ILQC_LAUNCH((forward_kernel<MI, 0>), n_threads, kBlock, st, m, B, n_threads, prob, x0, cmd, lin, traj, cost_t, total, cnorm);
   else
     ILQC_LAUNCH((forward_kernel<MI, 1>), n_threads, kBlock, st, m, B, n_threads, prob, x0, cmd, lin, traj, cost_t, total, cnorm);
+  return ILQC_LAUNCH_OK();
+}
+
+template <>
+int Launch<ILQC_MODEL_INST>::expand_parallel(const ilqc_model_desc& m, int B, int n_probs, const int32_t* prob,
+                                             const double* x0, const double* cmd, double* lin, double* traj, double* gsq,
+                                             double* cnorm, stream_t st) {
+  // trajectory (roll-out kernel, one thread per problem), then every step of every problem at once
+  ILQC_LAUNCH((forward_kernel<MI, 0>), n_probs, kBlock, st, m, B, n_probs, prob, x0, cmd, nullptr, traj, nullptr, nullptr, nullptr);
+  const long long n = (long long)n_probs * m.horizon;
+  ILQC_LAUNCH((expand_kernel<MI>), n, kBlock, st, m, B, n_probs, prob, traj, cmd, lin, gsq);
+  if (cnorm) ILQC_LAUNCH((cnorm_kernel<MI>), n_probs, 256, st, m, B, n_probs, prob, gsq, cnorm);
   return ILQC_LAUNCH_OK();
 }
 

@@ -448,7 +448,7 @@ ILQC_GLOBAL from_soa_kernel(const double* src, double* dst, int B, int n) {
 
 // ---- workspace ----------------------------------------------------------------------------------------
 struct Workspace {
-  double *lin, *traj, *hess, *gains, *diff, *dir, *newval, *diffsq, *jcst, *step_true, *step_roll, *reg, *curr_val,
+  double *lin, *traj, *hess, *gsq, *gains, *diff, *dir, *newval, *diffsq, *jcst, *step_true, *step_roll, *reg, *curr_val,
       *cnorm, *gnorm, *s_try, *dec_unit, *reg_prob;
   int32_t *prob, *gslot, *feas_slot, *feas_prob, *list, *flags, *trips, *count, *ident, *accept, *phase, *iter;
   size_t bytes;
@@ -530,7 +530,7 @@ inline size_t slot_capacity(int B, int Lmax) {
 }
 // quad: second-order algorithms also keep the second-order tensor of the dynamics [H][hess_stride][B]
 inline bool needs_hess(const ilqc_algo_desc* a) { return a->approx == ILQC_APPROX_QUAD && a->algo_type != ILQC_ALGO_GD; }
-inline void carve(Workspace* w, char* base, const Dims& d, int H, int B, int L, bool quad) {
+inline void carve(Workspace* w, char* base, const Dims& d, int H, int B, int L, bool quad, bool tpar = false) {
   size_t off = 0;
   auto takeD = [&](size_t n) { double* p = (double*)(base + off); off = align_up(off + n * sizeof(double)); return p; };
   auto takeI = [&](size_t n) { int32_t* p = (int32_t*)(base + off); off = align_up(off + n * sizeof(int32_t)); return p; };
@@ -538,6 +538,7 @@ inline void carve(Workspace* w, char* base, const Dims& d, int H, int B, int L, 
   w->lin = takeD((size_t)H * d.lin_stride * B);
   w->traj = takeD((size_t)(H + 1) * d.nx * B);
   w->hess = quad ? takeD((size_t)H * d.hess_stride * B) : nullptr;
+  w->gsq = tpar ? takeD((size_t)H * B) : nullptr;  // scratch of the time-parallel expansion
   w->gains = takeD((size_t)H * d.gain_stride * S);
   w->diff = takeD((size_t)H * d.nu * S);
   w->dir = takeD((size_t)H * d.nu * B);
@@ -559,10 +560,10 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
   Dims d;
   int rc = get_dims(m, &d);
   if (rc) return rc;
-  if (!a || B <= 0 || n_iter < 0 || a->n_candidates < 1) return ILQC_E_ARG;
+  if (!a || B <= 0 || n_iter < 0 || a->n_candidates < 1 || a->expansion < 0 || a->expansion > 1) return ILQC_E_ARG;
   const int H = m->horizon, L = a->n_candidates;
   Workspace w;
-  carve(&w, (char*)workspace, d, H, B, L, needs_hess(a));
+  carve(&w, (char*)workspace, d, H, B, L, needs_hess(a), a->expansion == 1);
   if (!workspace || workspace_bytes < w.bytes) return ILQC_E_WORKSPACE;
 
   ProfScope prof(st);
@@ -591,7 +592,8 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
   // iteration 0: objective of the initial controls (same arithmetic as every candidate evaluation), its
   // expansion and the metrics row 0 (run_min_algo.py:65-76)
   ILQC_PROF(PROF_FORWARD0, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(0, md, B, B, nullptr, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st))));
-  ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
+  if (a->expansion == 1) { ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::expand_parallel(md, B, B, nullptr, x0, cmd, w.lin, w.traj, w.gsq, w.cnorm, st)))); }
+  else { ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st)))); }
   if (quad) ILQC_PROF(PROF_LINEARIZE, 0, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, B, nullptr, w.traj, cmd, w.hess, st))));
   if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
   ILQC_LAUNCH((status_kernel), B, 256, st, P, B, 0, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
@@ -670,7 +672,8 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
     if (ls_trips) ILQC_CHECK(dev_d2d(ls_trips + (size_t)(it - 1) * B, w.trips, sizeof(int32_t) * B, st));
 
     // re-expand at the accepted controls (algos_steps.py:376-378) and collect the metrics of this iteration
-    ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st))));
+    if (a->expansion == 1) { ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::expand_parallel(md, B, B, nullptr, x0, cmd, w.lin, w.traj, w.gsq, w.cnorm, st)))); }
+    else { ILQC_PROF(PROF_LINEARIZE, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, B, nullptr, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, st)))); }
   if (quad) ILQC_PROF(PROF_LINEARIZE, 0, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, B, nullptr, w.traj, cmd, w.hess, st))));
     if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
     ILQC_LAUNCH((status_kernel), B, 256, st, P, B, it, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,

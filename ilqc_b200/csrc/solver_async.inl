@@ -49,6 +49,7 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
   if (!a || B <= 0 || n_iter < 0 || a->n_candidates < 1) return ILQC_E_ARG;
   const int H = m->horizon, L = a->n_candidates;
   Workspace w;
+  if (a->expansion != 0) return ILQC_E_UNSUPPORTED;  // the time-parallel expansion belongs to the lock-step driver
   carve(&w, (char*)workspace, d, H, B, L, needs_hess(a));
   if (!workspace || workspace_bytes < w.bytes) return ILQC_E_WORKSPACE;
 

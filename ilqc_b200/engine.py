@@ -272,7 +272,7 @@ class Engine:
 
     # ---- run_min_algo -------------------------------------------------------------------------------------
     def algo_desc(self, algo, n_candidates=1, line_search=True, compute_grad_norm=True, max_ls_trips=0, scheduler=0,
-                  handle_bad_dir="check_total_value"):
+                  handle_bad_dir="check_total_value", expansion=0):
         a = _lib.AlgoDesc()
         a.algo_type, a.approx, a.step_mode = parse_algo(algo)
         a.n_candidates = int(n_candidates)
@@ -283,6 +283,7 @@ class Engine:
         if handle_bad_dir not in _lib.BAD_DIR:   # 'modify_hess' is dead code in the reference (removed torch.eig)
             raise NotImplementedError(handle_bad_dir)
         a.handle_bad_dir = _lib.BAD_DIR[handle_bad_dir]
+        a.expansion = int(expansion)
         return a
 
     def workspace(self, nbytes):
@@ -293,7 +294,7 @@ class Engine:
 
     def solve(self, env, algo="ddp_linquad_reg", max_iter=10, x0=None, cmd0=None, stepsize=None, batch=None,
               weights=None, t0=None, horizon=None, n_candidates=128, line_search=True, compute_grad_norm=True,
-              record_trips=False, max_ls_trips=0, scheduler=0, handle_bad_dir="check_total_value"):
+              record_trips=False, max_ls_trips=0, scheduler=0, handle_bad_dir="check_total_value", expansion=0):
         """run_min_algo for a batch of problems of one family (device tensors in / out)."""
         if cmd0 is not None:
             cmd0 = self._dev(cmd0)
@@ -304,7 +305,7 @@ class Engine:
         x0 = self._x0(env, x0, B).reshape(B, -1)
         d, keep = self.make_desc(env, H, B, t0, weights)
         nx, nu = self.dims(d)
-        a = self.algo_desc(algo, n_candidates, line_search, compute_grad_norm, max_ls_trips, scheduler, handle_bad_dir)
+        a = self.algo_desc(algo, n_candidates, line_search, compute_grad_norm, max_ls_trips, scheduler, handle_bad_dir, expansion)
         cmds = self.to_soa(cmd0) if cmd0 is not None else torch.zeros(H * nu, B, dtype=F64, device=self.device)
         if stepsize is None:
             stepsize = default_stepsize(algo)

@@ -65,7 +65,7 @@ class MpcResult:
 def run_mpc_batched(env, full_horizon: int, window_size: int, overlap: int, max_iter: int = 10,
                     algo: str = "ddp_linquad_reg", x0=None, weights=None, batch=None, n_candidates: int = 128,
                     engine=None, max_windows: Optional[int] = None, optim_on_full_window: bool = False,
-                    keep_applying_last_ctrl: bool = True) -> MpcResult:
+                    keep_applying_last_ctrl: bool = True, expansion: Optional[int] = None) -> MpcResult:
     """B concurrent episodes of run_mpc (mpc_pipeline.py:87-115): horizon <- min(max(horizon + window_size -
     overlap, window_size), full_horizon) per window, each window = mpc_step with the previous window's result.
     The first window is solved on `env.horizon` steps like the reference (run_min_algo sizes cmd from
@@ -80,13 +80,18 @@ def run_mpc_batched(env, full_horizon: int, window_size: int, overlap: int, max_
     B = x0.shape[0]
     wts = None if weights is None else torch.as_tensor(weights, dtype=torch.float64).to(dev)
     sliding = window_size - overlap
+    if expansion is None:
+        # windows of a few thousand episodes do not fill the GPU: expand every time step of every episode at once
+        # (ilqc_algo_desc.expansion = 1) instead of walking each window's horizon in one thread
+        expansion = 1 if B <= 8192 else 0
     horizon, costs, stats, horizons, n_it = 0, [], [], [], 0
     cmd_hist = None                      # [B, T, nu]
     k_frozen, x_frozen = 0, x0           # state after the first k_frozen controls of cmd_hist
     while horizon < full_horizon:
         horizon = min(max(horizon + sliding, window_size), full_horizon)
         if cmd_hist is None:
-            r = run_min_algo_batched(env, max_iter, algo, x0=x0, weights=wts, t0=0, n_candidates=n_candidates, engine=eng)
+            r = run_min_algo_batched(env, max_iter, algo, x0=x0, weights=wts, t0=0, n_candidates=n_candidates, engine=eng,
+                                     expansion=expansion)
             cmd_hist = r.cmd
         else:
             curr = cmd_hist.shape[1]
@@ -95,7 +100,7 @@ def run_mpc_batched(env, full_horizon: int, window_size: int, overlap: int, max_
             if optim_on_full_window:
                 # the env keeps its initial state and time (mpc_pipeline.py:35-36); the window is the whole horizon
                 r = run_min_algo_batched(env, max_iter, algo, x0=x0, prev_cmd=torch.cat((cmd_hist, pad), dim=1), weights=wts,
-                                         t0=0, n_candidates=n_candidates, engine=eng)
+                                         t0=0, n_candidates=n_candidates, engine=eng, expansion=expansion)
                 cmd_hist = r.cmd
             else:
                 init_cmd = torch.cat((cmd_hist[:, curr - overlap:], pad), dim=1)
@@ -107,7 +112,7 @@ def run_mpc_batched(env, full_horizon: int, window_size: int, overlap: int, max_
                     traj, _, _ = eng.rollout_cost(env, x_frozen, cmd_hist[:, k_frozen:a_pos], t0=k_frozen, weights=wts)
                     x_frozen, k_frozen = traj[:, -1].contiguous(), a_pos
                 r = run_min_algo_batched(env, max_iter, algo, x0=x_frozen, prev_cmd=init_cmd, weights=wts, t0=a,
-                                         n_candidates=n_candidates, engine=eng)
+                                         n_candidates=n_candidates, engine=eng, expansion=expansion)
                 cmd_hist = torch.cat((cmd_hist[:, :-overlap], r.cmd), dim=1)  # prev_cmd[:-overlap] (mpc_pipeline.py:53)
         costs.append(r.cost)
         stats.append(r.status)

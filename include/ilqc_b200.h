@@ -97,6 +97,10 @@ typedef struct ilqc_algo_desc {
   int32_t scheduler;        /* 0 auto, 1 lock-step iterations, 2 asynchronous per-problem state machines
                                (regularised step modes and gd only); identical results either way */
   int32_t handle_bad_dir;   /* ILQC_BAD_DIR_* (run_min_algo(handle_bad_dir=...), run_min_algo.py:21) */
+  int32_t expansion;        /* 0: one thread per problem walks the horizon (roll-out + expansion fused; best for
+                               large batches).  1: time-parallel, for small batches (MPC windows, single problems):
+                               a roll-out pass stores the trajectory, then one thread per (problem, time step)
+                               expands its step.  Same mathematics; the two modes differ by rounding (1e-14). */
 } ilqc_algo_desc;
 
 int ilqc_abi_version(void);

@@ -309,3 +309,18 @@ def check_riccati_vs_dense_newton(eng, B=48, H=10, reg=0.3):
     err_j = relerr(bw["jcst"][:, 0], dec.numpy())
     assert err < 1e-8 and err_j < 1e-8, (err, err_j)
     return err, err_j
+
+
+def check_time_parallel_expansion(eng):
+    """ilqc_algo_desc.expansion = 1 (one thread per (problem, time step)) against the default fused kernel: same
+    mathematics, rounding-level differences only; and against the reference trace of the bicycle H=25 run."""
+    g = golden("run_bcar_h25_ddp_linquad_reg")
+    env = env_of(g)
+    x0 = t64(g["x0"]).reshape(1, -1).repeat(5, 1)
+    for algo in ("ddp_linquad_reg", "ddp_quad_reg", "classic_linquad_dir"):
+        a = eng.solve(env, algo, 3, x0=x0, record_trips=True)
+        b = eng.solve(env, algo, 3, x0=x0, record_trips=True, expansion=1)
+        assert relerr(b.cost, a.cost.cpu().numpy()) < 1e-10 and relerr(b.cmd, a.cmd.cpu().numpy()) < 1e-8, algo
+        assert torch.equal(a.ls_trips, b.ls_trips) and torch.equal(a.status, b.status), algo
+    b = eng.solve(env, "ddp_linquad_reg", 3, x0=x0, expansion=1)
+    assert relerr(b.cost[0], g["cost"][:4]) < TOL and relerr(b.cmd[0], g["cmds"][3]) < TOL

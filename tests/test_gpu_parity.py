@@ -275,3 +275,7 @@ def test_random_config_vs_oracle(cuda_engine, seed):
 def test_riccati_vs_dense_newton_batch(cuda_engine):
     """Dense cross-check (the idea of the reference's tests/test_auto_lin_quad.py) on a batch of bicycle problems."""
     pc.check_riccati_vs_dense_newton(cuda_engine, B=256)
+
+
+def test_time_parallel_expansion(cuda_engine):
+    pc.check_time_parallel_expansion(cuda_engine)

@@ -49,3 +49,7 @@ def test_random_config_vs_oracle(sim_engine, seed):
 
 def test_riccati_vs_dense_newton_batch(sim_engine):
     pc.check_riccati_vs_dense_newton(sim_engine)
+
+
+def test_time_parallel_expansion(sim_engine):
+    pc.check_time_parallel_expansion(sim_engine)
