@@ -258,7 +258,7 @@ int Launch<ILQC_MODEL_INST>::backward(int mode, const ilqc_model_desc& m, int B,
 #define ILQC_BWD_ARGS m, B, n_slots, prob, oslot, n_oslots, reg_ctrl, reg_state, lin, traj, cmd, hess, gains, jcst, feasible, bad_dir
   if (mode == ILQC_BWD_LINQUAD) {
     if constexpr (kBwdAsyncFeed<MI>) {
-      if (dense && n_slots <= 4 * B) {
+      if (dense && (long long)n_slots <= 5LL * B) {
         ILQC_LAUNCH_SMEM((backward_kernel<MI, ILQC_BWD_LINQUAD, true, false>), n_slots, kBlock, kBwdSmemBytes<MI>, st, ILQC_BWD_ARGS);
         return ILQC_LAUNCH_OK();
       }

@@ -127,6 +127,10 @@ namespace {
 struct LsParams {
   int algo_type, approx, step_mode, L, line_search, H, nu;
   double rho;
+  // variable candidate counts (asynchronous scheduler): candidates of active problem a occupy the slots
+  // [slot_off[a], slot_off[a] + slot_cnt[a]); NULL: uniform L, slots a * L + c
+  const int32_t* slot_cnt = nullptr;
+  const int32_t* slot_off = nullptr;
 };
 // per-problem scheduler state of the asynchronous driver (all NULL in the lock-step driver)
 enum { PHASE_LIN = 0, PHASE_LS = 1, PHASE_DONE = 2 };
@@ -208,8 +212,9 @@ ILQC_GLOBAL make_slots_kernel(LsParams P, int n_active, const int32_t* list, con
   const int b = list[a];
   double s = s_try[b];
   const bool regmode = (P.step_mode == ILQC_STEP_REG || P.step_mode == ILQC_STEP_REGVAR);
-  for (int c = 0; c < P.L; ++c) {
-    const int slot = a * P.L + c;
+  const int L = P.slot_cnt ? P.slot_cnt[a] : P.L, off = P.slot_off ? P.slot_off[a] : a * P.L;
+  for (int c = 0; c < L; ++c) {
+    const int slot = off + c;
     prob[slot] = b;
     step_true[slot] = s;
     if (P.algo_type == ILQC_ALGO_GD) {
@@ -243,8 +248,9 @@ ILQC_GLOBAL ls_select_kernel(LsParams P, int n_active, int B, int n_slots, const
   int chosen = -1;
   bool chosen_feasible = false;
   int ntrip = trips[b];
-  for (int c = 0; c < P.L && chosen < 0; ++c) {
-    const int slot = a * P.L + c;
+  const int L = P.slot_cnt ? P.slot_cnt[a] : P.L, off = P.slot_off ? P.slot_off[a] : a * P.L;
+  for (int c = 0; c < L && chosen < 0; ++c) {
+    const int slot = off + c;
     const double s = step_true[slot];
     bool feasible = true;
     if (P.algo_type != ILQC_ALGO_GD) feasible = regmode ? (feas_slot[slot] != 0) : (feas_prob[b] != 0);
@@ -269,7 +275,7 @@ ILQC_GLOBAL ls_select_kernel(LsParams P, int n_active, int B, int n_slots, const
   trips[b] = ntrip;
   accept[a] = -1;
   if (chosen >= 0) {
-    const int slot = a * P.L + chosen;
+    const int slot = off + chosen;
     if (chosen_feasible) {
       accept[a] = slot;  // cmd += diff[slot] is done by apply_kernel, coalesced over the active problems
       curr_val[b] = newval[slot];
@@ -297,7 +303,7 @@ ILQC_GLOBAL ls_select_kernel(LsParams P, int n_active, int B, int n_slots, const
     }
     flags[b] = 0;
   } else {
-    s_try[b] = step_true[a * P.L + P.L - 1] * P.rho;
+    s_try[b] = step_true[off + L - 1] * P.rho;
     flags[b] = 1;
   }
 }
@@ -313,6 +319,120 @@ ILQC_GLOBAL compact_eq_kernel(int B, const int32_t* phase, int value, int32_t* l
 #else
 __global__ void __launch_bounds__(1024) compact_eq_kernel(int B, const int32_t* phase, int value, int32_t* list, int32_t* count) {
   compact_block(B, [=](int b) { return phase[b] == value; }, list, count);
+}
+#endif
+
+// asynchronous scheduler, one tick: ordered lists of the problems in their line search (list) and of those
+// waiting for their re-expansion (ident), and for the former the number of candidates of this tick from the
+// trips already spent in the current search (round policy of round_candidates: 4, then 3, then 16, then 128 at
+// a time), their slot offsets and the total.  When the total would exceed the slot capacity every count is capped.
+ILQC_HD int tick_candidates(int trips_so_far) { return trips_so_far < 4 ? 4 : (trips_so_far < 7 ? 3 : (trips_so_far < 23 ? 16 : 128)); }
+#if defined(ILQC_HOSTSIM)
+ILQC_GLOBAL plan_async_kernel(int B, const int32_t* phase, const int32_t* trips, int Lmax, int cap, int32_t* list,
+                              int32_t* cnt, int32_t* off, int32_t* ident, int32_t* count) {
+  int cls[4] = {0, 0, 0, 0};
+  for (int b = 0; b < B; ++b)
+    if (phase[b] == PHASE_LS) { const int d = tick_candidates(trips[b]); ++cls[d == 4 ? 0 : (d == 3 ? 1 : (d == 16 ? 2 : 3))]; }
+  static const int caps[9] = {128, 64, 32, 16, 8, 4, 3, 2, 1};
+  int Lc = 1;
+  for (int i = 0; i < 9; ++i) {
+    const int c = caps[i];
+    const long long D = (long long)cls[0] * (4 < c ? 4 : c) + (long long)cls[1] * (3 < c ? 3 : c) +
+                        (long long)cls[2] * (16 < c ? 16 : c) + (long long)cls[3] * (128 < c ? 128 : c);
+    if (D <= cap) { Lc = c; break; }
+  }
+  int n_ls = 0, n_lin = 0, slots = 0;
+  for (int b = 0; b < B; ++b) {
+    if (phase[b] == PHASE_LS) {
+      int L = tick_candidates(trips[b]);
+      L = L < Lc ? L : Lc;
+      L = L < Lmax ? L : Lmax;
+      list[n_ls] = b; cnt[n_ls] = L; off[n_ls] = slots;
+      slots += L; ++n_ls;
+    } else if (phase[b] == PHASE_LIN) {
+      ident[n_lin++] = b;
+    }
+  }
+  count[0] = n_ls; count[1] = n_lin; count[2] = slots;
+}
+#else
+__global__ void __launch_bounds__(1024) plan_async_kernel(int B, const int32_t* phase, const int32_t* trips, int Lmax, int cap,
+                                                          int32_t* list, int32_t* cnt, int32_t* off, int32_t* ident,
+                                                          int32_t* count) {
+  __shared__ int w_ls[32], w_lin[32], w_slots[32], w_cls[32][4];
+  __shared__ int s_Lc;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int per = (((B + 31) / 32) + 31) & ~31;
+  const int lo = wid * per, hi = min(B, lo + per);
+  // pass 1: members and candidate classes of this warp's range
+  int n_ls = 0, n_lin = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  for (int base = lo; base < hi; base += 32) {
+    const int b = base + lane;
+    const int ph = b < hi ? phase[b] : -1;
+    const bool ls = ph == PHASE_LS;
+    const int d = ls ? tick_candidates(trips[b]) : 0;
+    n_ls += __popc(__ballot_sync(0xffffffffu, ls));
+    n_lin += __popc(__ballot_sync(0xffffffffu, ph == PHASE_LIN));
+    c0 += __popc(__ballot_sync(0xffffffffu, d == 4));
+    c1 += __popc(__ballot_sync(0xffffffffu, d == 3));
+    c2 += __popc(__ballot_sync(0xffffffffu, d == 16));
+    c3 += __popc(__ballot_sync(0xffffffffu, d == 128));
+  }
+  if (lane == 0) { w_ls[wid] = n_ls; w_lin[wid] = n_lin; w_cls[wid][0] = c0; w_cls[wid][1] = c1; w_cls[wid][2] = c2; w_cls[wid][3] = c3; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long cls[4] = {0, 0, 0, 0};
+    for (int w = 0; w < 32; ++w)
+      for (int k = 0; k < 4; ++k) cls[k] += w_cls[w][k];
+    const int caps[9] = {128, 64, 32, 16, 8, 4, 3, 2, 1};
+    int Lc = 1;
+    for (int i = 0; i < 9; ++i) {
+      const int c = caps[i];
+      const long long D = cls[0] * min(4, c) + cls[1] * min(3, c) + cls[2] * min(16, c) + cls[3] * min(128, c);
+      if (D <= cap) { Lc = c; break; }
+    }
+    s_Lc = Lc;
+  }
+  __syncthreads();
+  const int Lc = s_Lc;
+  // pass 2: slots of this warp's range
+  int slots = 0;
+  for (int base = lo; base < hi; base += 32) {
+    const int b = base + lane;
+    int L = (b < hi && phase[b] == PHASE_LS) ? min(min(tick_candidates(trips[b]), Lc), Lmax) : 0;
+    for (int o = 16; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
+    slots += L;
+  }
+  if (lane == 0) w_slots[wid] = slots;
+  __syncthreads();
+  int pos_ls = 0, pos_lin = 0, pos_slot = 0, tot_ls = 0, tot_lin = 0, tot_slot = 0;
+  for (int w = 0; w < 32; ++w) {
+    if (w < wid) { pos_ls += w_ls[w]; pos_lin += w_lin[w]; pos_slot += w_slots[w]; }
+    tot_ls += w_ls[w]; tot_lin += w_lin[w]; tot_slot += w_slots[w];
+  }
+  // pass 3: ordered lists, counts and offsets
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = lo; base < hi; base += 32) {
+    const int b = base + lane;
+    const int ph = b < hi ? phase[b] : -1;
+    const bool ls = ph == PHASE_LS, lin = ph == PHASE_LIN;
+    const int L = ls ? min(min(tick_candidates(trips[b]), Lc), Lmax) : 0;
+    int incl = L;  // inclusive warp scan of L
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const unsigned m_ls = __ballot_sync(0xffffffffu, ls), m_lin = __ballot_sync(0xffffffffu, lin);
+    if (ls) {
+      const int a = pos_ls + __popc(m_ls & lt);
+      list[a] = b; cnt[a] = L; off[a] = pos_slot + incl - L;
+    }
+    if (lin) ident[pos_lin + __popc(m_lin & lt)] = b;
+    pos_ls += __popc(m_ls);
+    pos_lin += __popc(m_lin);
+    pos_slot += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (threadIdx.x == 0) { count[0] = tot_ls; count[1] = tot_lin; count[2] = tot_slot; }
 }
 #endif
 
@@ -450,7 +570,8 @@ ILQC_GLOBAL from_soa_kernel(const double* src, double* dst, int B, int n) {
 struct Workspace {
   double *lin, *traj, *hess, *gsq, *gains, *diff, *dir, *newval, *diffsq, *jcst, *step_true, *step_roll, *reg, *curr_val,
       *cnorm, *gnorm, *s_try, *dec_unit, *reg_prob;
-  int32_t *prob, *gslot, *feas_slot, *feas_prob, *list, *flags, *trips, *count, *ident, *accept, *phase, *iter;
+  int32_t *prob, *gslot, *feas_slot, *feas_prob, *list, *flags, *trips, *count, *ident, *accept, *phase, *iter, *slot_cnt,
+      *slot_off;
   size_t bytes;
 };
 inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -524,7 +645,8 @@ inline int round_candidates(int round, int n_active, int Lmax) {
 }
 // slots the workspace must hold: n_active * round_candidates(...) <= max(B, largest round capacity)
 inline size_t slot_capacity(int B, int Lmax) {
-  size_t cap = (size_t)B * Lmax, wave = round_capacity(0);
+  // (two waves: round 0 of the bulk = 1.75 waves + the deferred stragglers of the asynchronous scheduler)
+  size_t cap = (size_t)B * Lmax, wave = 2 * (size_t)wave_slots();
   size_t s = cap < wave ? cap : wave;
   return s < (size_t)B ? (size_t)B : s;
 }
@@ -548,7 +670,7 @@ inline void carve(Workspace* w, char* base, const Dims& d, int H, int B, int L, 
   w->reg_prob = takeD(B);
   w->prob = takeI(S); w->gslot = takeI(S); w->feas_slot = takeI(S);
   w->feas_prob = takeI(B); w->list = takeI(B); w->flags = takeI(B); w->trips = takeI(B); w->ident = takeI(B); w->accept = takeI(B);
-  w->phase = takeI(B); w->iter = takeI(B);
+  w->phase = takeI(B); w->iter = takeI(B); w->slot_cnt = takeI(B); w->slot_off = takeI(B);
   w->count = takeI(64);
   w->bytes = off;
 }

@@ -79,6 +79,9 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
 #endif
 #define ILQC_CHECK(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
+  // stragglers allowed to lag behind the bulk: ~2 % of the batch, at least one block's worth
+  int lag = B / 50 < 64 ? 64 : B / 50;
+  if (const char* e = getenv("ILQC_LAG")) lag = atoi(e);  // tuning knob
   const int n_rows = (n_iter + 1) * B;
   ILQC_LAUNCH((fill_i32_kernel), B, 256, st, B, status, (int32_t)ILQC_RUNNING);
   ILQC_LAUNCH((fill_i32_kernel), B, 256, st, B, n_done, (int32_t)0);
@@ -94,18 +97,24 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
   ILQC_PROF(PROF_FORWARD0, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(0, md, B, B, nullptr, x0, cmd, nullptr, nullptr, nullptr, w.curr_val, nullptr, st))));
 
   for (;;) {
-    ILQC_LAUNCH((compact_eq_kernel), 1, 1024, st, B, w.phase, (int)PHASE_LS, w.list, w.count);
-    ILQC_LAUNCH((compact_eq_kernel), 1, 1024, st, B, w.phase, (int)PHASE_LIN, w.ident, w.count + 1);
-    int counts[2] = {0, 0};
-    ILQC_CHECK(dev_d2h_sync(counts, w.count, 2 * sizeof(int), st));
-    const int n_ls = counts[0], n_lin = counts[1];
+    ILQC_LAUNCH((plan_async_kernel), 1, 1024, st, B, w.phase, w.trips, L, (int)slot_capacity(B, L), w.list, w.slot_cnt, w.slot_off,
+                w.ident, w.count);
+    int counts[3] = {0, 0, 0};
+    ILQC_CHECK(dev_d2h_sync(counts, w.count, 3 * sizeof(int), st));
+    const int n_ls = counts[0], n_lin = counts[1], n_slots = counts[2];
     if (n_ls == 0 && n_lin == 0) break;
+    // Bulk-synchronous with deferred stragglers: the accepted problems wait for their (full-size, efficient)
+    // re-expansion until at most `lag` problems are still searching; those stragglers then keep searching on
+    // stream A while stream B re-expands the bulk, and join the bulk's next rounds with their own (wider)
+    // candidate counts, one iteration behind.  The lock-step driver instead spends 2 latency-bound rounds per
+    // iteration on them with the rest of the GPU idle.
+    const bool do_lin = n_lin > 0 && n_ls <= lag;
 #if !defined(ILQC_HOSTSIM)
     cudaEventRecord(ss.ev_a, st);
     cudaStreamWaitEvent(sb, ss.ev_a, 0);
 #endif
     // ---- stream B: re-expansion, gradient, metrics row and next line-search set-up of the LIN problems ----
-    if (n_lin > 0) {
+    if (do_lin) {
       ILQC_PROF_ON(sb, PROF_LINEARIZE, n_lin, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::forward(1, md, B, n_lin, w.ident, x0, cmd, w.lin, w.traj, nullptr, nullptr, w.cnorm, sb))));
       if (quad) ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, n_lin, w.ident, w.traj, cmd, w.hess, sb)));
       if (need_grad) ILQC_PROF_ON(sb, PROF_ADJOINT, n_lin, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, n_lin, w.ident, w.lin, w.dir, w.gnorm, sb))));
@@ -114,14 +123,15 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
     }
     // ---- stream A: line-search candidates of the LS problems ----
     if (n_ls > 0) {
-      P.L = round_candidates(-1, n_ls, L);
-      const int n_slots = n_ls * P.L;
+      P.L = 0;
+      P.slot_cnt = w.slot_cnt;
+      P.slot_off = w.slot_off;
       ILQC_LAUNCH((make_slots_kernel), n_ls, 256, st, P, n_ls, w.list, w.s_try, w.prob, w.gslot, w.step_true, w.step_roll, w.reg);
       if (a->algo_type == ILQC_ALGO_GD) {
         ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::rollout(ILQC_ROLL_GD, md, B, n_slots, w.prob, nullptr, 0, nullptr, n_slots, w.step_roll, x0,
                                                         cmd, w.traj, w.lin, nullptr, w.dir, w.diff, w.newval, w.diffsq, st))));
       } else {
-        ILQC_PROF(PROF_BACKWARD, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::backward(bwd_mode, md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
+        ILQC_PROF(PROF_BACKWARD, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::backward(bwd_mode | ((size_t)n_ls * 10 >= (size_t)B * 9 ? ILQC_BWD_DENSE_HINT : 0), md, B, n_slots, w.prob, nullptr, n_slots, w.reg, 0.0, w.lin, w.traj, cmd,
                                                          w.hess, w.gains, w.jcst, w.feas_slot, st))));
         const int kind = a->algo_type == ILQC_ALGO_DDP ? ILQC_ROLL_EXACT : ILQC_ROLL_LIN;
         ILQC_PROF(PROF_ROLLOUT, n_slots, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::rollout(kind, md, B, n_slots, w.prob, nullptr, n_slots, nullptr, n_slots, w.step_roll, x0, cmd,
