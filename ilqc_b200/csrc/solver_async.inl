@@ -109,6 +109,7 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
     // candidate counts, one iteration behind.  The lock-step driver instead spends 2 latency-bound rounds per
     // iteration on them with the rest of the GPU idle.
     const bool do_lin = n_lin > 0 && n_ls <= lag;
+    if (trace_rounds()) fprintf(stderr, "ilqc tick: ls %d lin %d slots %d do_lin %d\n", n_ls, n_lin, n_slots, (int)do_lin);
 #if !defined(ILQC_HOSTSIM)
     cudaEventRecord(ss.ev_a, st);
     cudaStreamWaitEvent(sb, ss.ev_a, 0);
