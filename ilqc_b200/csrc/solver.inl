@@ -15,6 +15,7 @@
 // is one 4-byte counter per line-search round.
 #pragma once
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -602,6 +603,10 @@ inline int wave_slots() {
 #endif
 }
 // ILQC_TRACE_ROUNDS=1: one stderr line per line-search round (tuning aid)
+inline double trace_ms() {  // host clock, ms since the first call
+  static const auto t0 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
 inline bool trace_rounds() {
   static int v = -1;
   if (v < 0) v = getenv("ILQC_TRACE_ROUNDS") ? 1 : 0;
@@ -765,7 +770,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
     for (int round = 0; n_active > 0; ++round) {
       P.L = round_candidates(round, n_active, L);
       const int n_slots = n_active * P.L;
-      if (trace_rounds()) fprintf(stderr, "ilqc round: iter %d active %d candidates %d\n", it, n_active, P.L);
+      if (trace_rounds()) fprintf(stderr, "ilqc round: t %.3f ms iter %d active %d candidates %d\n", trace_ms(), it, n_active, P.L);
       ILQC_LAUNCH((make_slots_kernel), n_active, 256, st, P, n_active, w.list, w.s_try, w.prob, w.gslot, w.step_true,
                   w.step_roll, w.reg);
       if (a->algo_type == ILQC_ALGO_GD) {

@@ -109,7 +109,7 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
     // candidate counts, one iteration behind.  The lock-step driver instead spends 2 latency-bound rounds per
     // iteration on them with the rest of the GPU idle.
     const bool do_lin = n_lin > 0 && n_ls <= lag;
-    if (trace_rounds()) fprintf(stderr, "ilqc tick: ls %d lin %d slots %d do_lin %d\n", n_ls, n_lin, n_slots, (int)do_lin);
+    if (trace_rounds()) fprintf(stderr, "ilqc tick: t %.3f ms ls %d lin %d slots %d do_lin %d\n", trace_ms(), n_ls, n_lin, n_slots, (int)do_lin);
 #if !defined(ILQC_HOSTSIM)
     cudaEventRecord(ss.ev_a, st);
     cudaStreamWaitEvent(sb, ss.ev_a, 0);
@@ -123,7 +123,9 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
                   w.s_try, w.dec_unit, w.trips, status, A);
     }
     // ---- stream A: line-search candidates of the LS problems ----
-    if (n_ls > 0) {
+    // (ILQC_DEFER=1: the stragglers skip the re-expansion tick and continue inside the bulk's next big launch)
+    static const bool defer = getenv("ILQC_DEFER") != nullptr;
+    if (n_ls > 0 && !(defer && do_lin)) {
       P.L = 0;
       P.slot_cnt = w.slot_cnt;
       P.slot_off = w.slot_off;
