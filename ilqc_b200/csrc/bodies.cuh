@@ -269,22 +269,43 @@ template <class M, int NG, int G>
 ILQC_HD void hess_body(const ilqc_model_desc& m, int b, int B, int t, const double* __restrict__ traj,
                        const double* __restrict__ cmd, double* __restrict__ hess) {
   constexpr int NX = M::NX, NU = M::NU, NH = sym_size(M::NV);
-  using S = Jet<M::NV, 2, NG, G>;  // group G of NG groups of Hessian entries (jet.cuh)
+  constexpr int R = M::kRotVar;                  // heading variable, handled in closed form (models.cuh), or -1
+  constexpr int NVJ = R >= 0 ? M::NV - 1 : M::NV;  // jet variables actually carried
+  using S = Jet<NVJ, 2, NG, G>;  // group G of NG groups of Hessian entries (jet.cuh)
   double x[NX], u[NU];
 #pragma unroll
   for (int i = 0; i < NX; ++i) x[i] = traj[((size_t)t * NX + i) * B + b];
 #pragma unroll
   for (int k = 0; k < NU; ++k) u[k] = cmd[((size_t)t * NU + k) * B + b];
+  // jet index without the heading variable
+  auto red = [](int v) constexpr { return (v < 0 || v == R) ? -1 : ((R >= 0 && v > R) ? v - 1 : v); };
   S xs[NX], us[NU], xns[NX];
-  static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], M::sv(I)); });
-  static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], M::uv(I)); });
+  static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], red(M::sv(I))); });
+  static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], red(M::uv(I))); });
   M::template step<S>(m, xs, us, xns);
   double* T = hess + (size_t)t * Layout<M>::hess_stride * B + b;
-#pragma unroll
-  for (int i = 0; i < M::NXH; ++i)
-#pragma unroll
-    for (int k = 0; k < S::NH; ++k)
-      if (S::valid(k)) T[(size_t)(i * NH + S::entry(k)) * B] = xns[i].h[k];
+  static_for<M::NXH>([&](auto I) {
+    constexpr int i = I;
+    static_for<NH>([&](auto E) {
+      constexpr int e = E;                                   // packed entry (p, q), p <= q, over all NV variables
+      constexpr int p = SymTable<M::NV>().i[e], q = SymTable<M::NV>().j[e];
+      if constexpr (p != R && q != R) {
+        constexpr int er = sym_idx(red(p), red(q), NVJ);    // the same pair among the carried variables
+        if constexpr (er >= S::E0 && er < S::E0 + S::NH) T[(size_t)(i * NH + e) * B] = xns[i].h[er - S::E0];
+      } else if constexpr (G == 0) {
+        // entries with the heading: rows 0, 1 are (x, y); d/dphi (x' - x) = -(y' - y), d/dphi (y' - y) = x' - x
+        double v = 0.0;
+        if constexpr (i == 0) {
+          if constexpr (p == R && q == R) v = -(xns[0].v - x[0]);
+          else v = -xns[1].g[red(p == R ? q : p)];
+        } else if constexpr (i == 1) {
+          if constexpr (p == R && q == R) v = -(xns[1].v - x[1]);
+          else v = xns[0].g[red(p == R ? q : p)];
+        }
+        T[(size_t)(i * NH + e) * B] = v;
+      }
+    });
+  });
 }
 
 // ----------------------------------------------------------------------------------------------------

@@ -96,7 +96,7 @@ ILQC_GLOBAL cnorm_kernel(ilqc_model_desc m, int B, int n_probs, const int32_t* p
 #define ILQC_HESS_GROUPS 3
 #endif
 template <class M>
-constexpr int kHessGroups = sym_size(M::NV) > 16 ? ILQC_HESS_GROUPS : 1;
+constexpr int kHessGroups = sym_size(M::kRotVar >= 0 ? M::NV - 1 : M::NV) > 12 ? ILQC_HESS_GROUPS : 1;
 template <class M, int NG, int G>
 ILQC_GLOBAL_LB(ILQC_LB_BWD) hess_kernel(ilqc_model_desc m, int B, int n_probs, const int32_t* prob, const double* traj,
                                         const double* cmd, double* hess) {

@@ -264,6 +264,7 @@ template <>
 struct Model<ILQC_MODEL_PENDULUM> {
   static constexpr int NX = 2, NU = 1, NV = 3, NVC = 2;
   static constexpr int NXH = NX;  // state rows whose dynamics can have non-zero second derivatives
+  static constexpr int kRotVar = -1;  // no heading variable (see CarSimpleT)
   static constexpr int sv(int i) { constexpr int t[NX] = {0, 1}; return t[i]; }
   static constexpr int uv(int i) { constexpr int t[NU] = {2}; return t[i]; }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1}; return t[i]; }
@@ -319,6 +320,7 @@ struct CartPoleT {
   static constexpr int NSET = VAR ? 3 : 1;
   static constexpr int NX = 4, NU = NSET, NV = 3 + NSET, NVC = 3;
   static constexpr int NXH = NX;
+  static constexpr int kRotVar = -1;
   static constexpr int sv(int i) { constexpr int t[NX] = {-1, 0, 1, 2}; return t[i]; }
   static constexpr int uv(int i) { return 3 + i; }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1, -1, 2}; return t[i]; }
@@ -620,6 +622,11 @@ struct CarSimpleT {
   static constexpr int NSET = VAR ? 3 : 1;
   static constexpr int NX = 6, NU = 3 * NSET, NV = 2 + 2 * NSET, NVC = 4;
   static constexpr int NXH = 4;  // (tref, vtref) evolve linearly
+  // jet index of the heading phi.  (x' - x, y' - y) = R(phi) w with w independent of phi (phi enters the dynamics only
+  // through the rotation of the velocity, and phi' - phi does not depend on phi), so every derivative wrt phi is a
+  // rotation of quantities the other variables already give: d(x'-x)/dphi = -(y'-y), d(y'-y)/dphi = x'-x.  The
+  // Hessian-tensor kernel therefore runs its second-order jets without phi (hess_body).
+  static constexpr int kRotVar = 0;
   static constexpr int sv(int i) { constexpr int t[NX] = {-1, -1, 0, 1, -1, -1}; return t[i]; }
   static constexpr int uv(int k) { return (k % 3 == 2) ? -1 : 2 + 2 * (k / 3) + (k % 3); }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1, -1, -1, 2, 3}; return t[i]; }
@@ -726,6 +733,7 @@ struct CarBicycleT {
   static constexpr int NSET = VAR ? 3 : 1;
   static constexpr int NX = 8, NU = 3 * NSET, NV = 4 + 2 * NSET, NVC = 4;
   static constexpr int NXH = 6;  // (tref, vtref) evolve linearly
+  static constexpr int kRotVar = 0;  // heading phi, see CarSimpleT
   static constexpr int sv(int i) { constexpr int t[NX] = {-1, -1, 0, 1, 2, 3, -1, -1}; return t[i]; }
   static constexpr int uv(int k) { return (k % 3 == 2) ? -1 : 4 + 2 * (k / 3) + (k % 3); }
   static constexpr int cv(int i) { constexpr int t[NX] = {0, 1, -1, -1, -1, -1, 2, 3}; return t[i]; }
