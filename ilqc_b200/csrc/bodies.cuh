@@ -27,10 +27,15 @@ ILQC_HD void expand_step(const ilqc_model_desc& m, const Weights& w, const doubl
   using L = Layout<M>;
   constexpr int NX = M::NX, NU = M::NU;
   {
-    using S = Jet<M::NV, 1>;
+    // first-order jets over the model's active variables; the heading (M::kRotVar) is not one of them: its column of
+    // the Jacobian is a rotation of the position increments (models.cuh)
+    constexpr int R = M::kRotVar;
+    constexpr int NVJ = R >= 0 ? M::NV - 1 : M::NV;
+    using S = Jet<NVJ, 1>;
+    auto red = [](int v) constexpr { return (v < 0 || v == R) ? -1 : ((R >= 0 && v > R) ? v - 1 : v); };
     S xs[NX], us[NU], xns[NX];
-    static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], M::sv(I)); });
-    static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], M::uv(I)); });
+    static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], red(M::sv(I))); });
+    static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], red(M::uv(I))); });
     M::template step<S>(m, xs, us, xns);
 #pragma unroll
     for (int i = 0; i < NX; ++i) xn[i] = xns[i].v;
@@ -41,7 +46,8 @@ ILQC_HD void expand_step(const ilqc_model_desc& m, const Weights& w, const doubl
         constexpr int j = Jc;
         if constexpr (M::Nm(i, j)) {
           double v;
-          if constexpr (M::sv(j) >= 0) v = xns[i].g[M::sv(j)] - (i == j ? 1.0 : 0.0);
+          if constexpr (R >= 0 && M::sv(j) == R) v = (i == 0) ? -(xn[1] - x[1]) : ((i == 1) ? (xn[0] - x[0]) : 0.0);
+          else if constexpr (M::sv(j) >= 0) v = xns[i].g[red(M::sv(j))] - (i == j ? 1.0 : 0.0);
           else v = passive_N_of<M>(m, i, j);
           store(L::oN + M::Nm.slot(i, j), v);
         }
@@ -50,7 +56,7 @@ ILQC_HD void expand_step(const ilqc_model_desc& m, const Weights& w, const doubl
         constexpr int k = Kc;
         if constexpr (M::Bm(i, k)) {
           double v;
-          if constexpr (M::uv(k) >= 0) v = xns[i].g[M::uv(k)];
+          if constexpr (M::uv(k) >= 0) v = xns[i].g[red(M::uv(k))];
           else v = passive_B_of<M>(m, i, k);
           store(L::oB + M::Bm.slot(i, k), v);
         }
