@@ -51,7 +51,7 @@ CLASSES = ["rollout_cost", "linearize", "backward", "rollout_candidate", "adjoin
 # (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on, profiles/r01_ncu_hot_kernels_v3.txt).  The convention
 # above counts a transcendental or a division as ONE flop (each is 10-40 FP64 instructions) and the Riccati step
 # as dense 8x8 algebra (the kernel skips the structural zeros), so both views are reported.
-EXEC_FLOPS_PER_STEP = {"rollout_cost": 2000, "linearize": 4783, "backward": 1495, "rollout_candidate": 2115, "adjoint": 176}
+EXEC_FLOPS_PER_STEP = {"rollout_cost": 2000, "linearize": 4604, "backward": 1495, "rollout_candidate": 2115, "adjoint": 176}
 # DRAM bytes per slot per launch of the same ncu capture (dram__bytes_read.sum + dram__bytes_write.sum of a
 # 131072-slot launch = 4 candidates for each of 32768 problems; per-problem rows are shared by the candidates)
 NCU_DRAM_BYTES_PER_SLOT = {"rollout_candidate": 26350, "backward": 31900, "linearize": 50100}
