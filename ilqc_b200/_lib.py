@@ -10,6 +10,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 CUDA_LIB_PATH = os.path.join(PKG, "libilqc_b200.so")
 
+ABI_VERSION = 2
 # enums of include/ilqc_b200.h
 MODEL_PENDULUM, MODEL_CARTPOLE, MODEL_CAR_SIMPLE, MODEL_CAR_BICYCLE = 0, 1, 2, 3
 INT_EULER, INT_RK4_CST, INT_RK4 = 0, 1, 2
@@ -49,8 +50,9 @@ class ModelDesc(C.Structure):
 
 class AlgoDesc(C.Structure):
     """struct ilqc_algo_desc (include/ilqc_b200.h)."""
-    _fields_ = [(n, _i) for n in ("algo_type", "approx", "step_mode", "n_candidates", "line_search",
-                                  "max_ls_trips", "compute_grad_norm", "scheduler", "handle_bad_dir", "expansion")]
+    _fields_ = ([(n, _i) for n in ("algo_type", "approx", "step_mode", "n_candidates", "line_search",
+                                   "max_ls_trips", "compute_grad_norm", "scheduler", "handle_bad_dir", "expansion",
+                                   "reserved1", "reserved2")] + [("pp_cost0", _p)])
 
 
 _MP, _AP = C.POINTER(ModelDesc), C.POINTER(AlgoDesc)
@@ -73,6 +75,9 @@ PROTOTYPES = {
     "ilqc_solve": (C.c_int, [_MP, _AP, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "ilqc_solve_host_workspace_bytes": (C.c_size_t, [_MP, _AP, C.c_int, C.c_int]),
     "ilqc_solve_host": (C.c_int, [_MP, _AP, C.c_int, _p, _p, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "ilqc_mpc_num_windows": (C.c_int, [C.c_int] * 3),
+    "ilqc_mpc_workspace_bytes": (C.c_size_t, [_MP, _AP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ilqc_mpc": (C.c_int, [_MP, _AP, C.c_int, _p] + [C.c_int] * 7 + [_p, C.POINTER(_i), _p, _p, _p, _p, C.c_size_t, _p]),
     "ilqc_to_soa": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
     "ilqc_from_soa": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
     "ilqc_profile_enable": (C.c_int, [C.c_int]),
@@ -90,7 +95,7 @@ def bind(path):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.ilqc_abi_version() != 1:
+    if lib.ilqc_abi_version() != ABI_VERSION:
         raise RuntimeError("ilqc_b200: ABI version mismatch in %s" % path)
     return lib
 

@@ -1,1 +1,3 @@
 from .run_min_algo import run_min_algo, run_min_algo_batched, check_cvg_status, check_nomenclature
+from .algos_steps import (gd_oracle, newton_oracle, classic_oracle, ddp_oracle, min_step,
+                          backtracking_line_search)

@@ -47,7 +47,7 @@ def check_cvg_status(metrics: dict, verbose: bool = True) -> str:
 def run_min_algo_batched(env, max_iter: int = 10, algo: str = "ddp_linquad_reg", stepsize=None,
                          line_search: bool = True, handle_bad_dir: str = "check_total_value", x0=None,
                          prev_cmd=None, weights=None, t0=None, batch=None, n_candidates: int = 128,
-                         compute_grad_norm: bool = True, engine=None, expansion: int = 0):
+                         compute_grad_norm: bool = True, engine=None, expansion: int = 0, cost0=None):
     """B problems at once.  x0 [B,nx], prev_cmd [B,H,nu] (None: zeros), stepsize float or [B], weights [B,3]
     (Car reg_cont/reg_lag/reg_speed), t0 int or [B] (init_time_iter).  Returns ilqc_b200.engine.SolveResult
     with device tensors: cmd [B,H,nu], stepsize [B], cost / norm_grad_obj / stepsize_reported [B,max_iter+1],
@@ -59,7 +59,7 @@ def run_min_algo_batched(env, max_iter: int = 10, algo: str = "ddp_linquad_reg",
     return eng.solve(env, algo, max_iter, x0=x0, cmd0=prev_cmd, stepsize=stepsize, batch=batch, weights=weights,
                      t0=env.init_time_iter if t0 is None else t0, n_candidates=n_candidates,
                      line_search=line_search, compute_grad_norm=compute_grad_norm, handle_bad_dir=handle_bad_dir,
-                     expansion=expansion)
+                     expansion=expansion, cost0=cost0)
 
 
 def run_min_algo(env, max_iter: int = 10, algo: str = "ddp_linquad_reg", stepsize: Optional[float] = None,
@@ -86,8 +86,10 @@ def run_min_algo(env, max_iter: int = 10, algo: str = "ddp_linquad_reg", stepsiz
     n = max(max_iter - it0, 0)
     cmd0 = None if prev_cmd is None else torch.as_tensor(prev_cmd, dtype=torch.float64).detach().unsqueeze(0)
     tic = time.time()
+    # restart: divergence is tested against the ORIGINAL first cost (run_min_algo.py:240-243)
+    cost0 = None if past_metrics is None else torch.tensor([past_metrics["cost"][0]], dtype=torch.float64)
     r = run_min_algo_batched(env, n, algo, stepsize, line_search, handle_bad_dir, x0=env.init_state.reshape(1, -1),
-                             prev_cmd=cmd0, batch=1)
+                             prev_cmd=cmd0, batch=1, cost0=cost0)
     wall = time.time() - tic
     done = int(r.n_done[0])
     cost, gn, srep = r.cost[0].cpu().tolist(), r.norm_grad_obj[0].cpu().tolist(), r.stepsize_reported[0].cpu().tolist()

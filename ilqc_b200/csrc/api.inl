@@ -4,6 +4,7 @@
 #include "fastmath.cuh"
 #include "solver.inl"
 #include "solver_async.inl"
+#include "mpc.inl"
 
 namespace ilqc {
 int dense_lq_backward(int nx, int nu, int H, int B, int L, const double* A, const double* Bm, const double* p,
@@ -47,8 +48,9 @@ static int solve_dispatch(const ilqc_model_desc* m, const ilqc_algo_desc* a, int
   if (!a) return ILQC_E_ARG;
   const bool regmode = a->algo_type == ILQC_ALGO_GD || a->step_mode == ILQC_STEP_REG || a->step_mode == ILQC_STEP_REGVAR;
   int sched = a->scheduler;
-  (void)regmode;
+  if (sched < 0 || sched > 2) return ILQC_E_ARG;
   if (sched == 0) sched = 1;
+  if (sched == 2 && !regmode) return ILQC_E_UNSUPPORTED;  // direction oracles: lock-step driver only
   if (sched == 2)
     return solve_async_impl(m, a, B, x0, cmd, stepsize, n_iter, cost, gnorm, step_rep, n_done, status, ls_trips,
                             workspace, workspace_bytes, st);
@@ -164,7 +166,7 @@ int ilqc_grad_obj(const ilqc_model_desc* m, int B, const double* lin, double* gr
   int rc = get_dims(m, &d);
   if (rc) return rc;
   if (B <= 0 || !lin || !gnorm) return ILQC_E_ARG;
-  (void)cnorm;
+  if (cnorm) ILQC_FOR_MODEL(effective_model(*m), { int rc2 = LM::cnorm_lin(*m, B, lin, cnorm, (stream_t)stream); if (rc2) return rc2; });
   ILQC_FOR_MODEL(effective_model(*m), return LM::adjoint(*m, B, B, nullptr, lin, grad, gnorm, (stream_t)stream));
   return 0;
 }
@@ -280,6 +282,134 @@ int ilqc_solve_host(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, co
   ILQC_CHECK(dev_sync(st));
 #undef ILQC_CHECK
   return 0;
+}
+
+// ---- closed-loop MPC episodes ----------------------------------------------------------------------------
+int ilqc_mpc_num_windows(int full_horizon, int window_size, int overlap) {
+  if (full_horizon <= 0 || window_size <= 0 || overlap < 0 || overlap >= window_size) return ILQC_E_ARG;
+  int n = 0;
+  for (int h = 0; h < full_horizon; ++n) h = mpc_next_horizon(h, window_size, overlap, full_horizon);
+  return n;
+}
+// walks the window sequence on the host: longest solve horizon (and validity of every window)
+static int mpc_max_window(int first_h, int full_horizon, int window_size, int overlap, bool full) {
+  int curr = 0, maxH = first_h;
+  for (int h = 0; h < full_horizon;) {
+    h = mpc_next_horizon(h, window_size, overlap, full_horizon);
+    if (curr == 0) { curr = first_h; continue; }
+    MpcWindow w;
+    if (!mpc_window(curr, h, overlap, full, &w) || w.Hw <= 0) return -1;
+    if (w.Hw > maxH) maxH = w.Hw;
+    curr = w.keep + w.Hw;
+  }
+  return maxH;
+}
+enum { kMpcAdvanceChunk = 16 };
+struct MpcCarve { size_t solve, wcmd, xfrozen, traj, step, met, ints, total; };
+static bool mpc_carve(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, int full_horizon, int window_size,
+                      int overlap, int max_iter, int full, MpcCarve* c, int* maxH_out) {
+  Dims d;
+  if (get_dims(m, &d) || !a || B <= 0 || max_iter < 0) return false;
+  if (ilqc_mpc_num_windows(full_horizon, window_size, overlap) <= 0) return false;
+  const int maxH = mpc_max_window(m->horizon, full_horizon, window_size, overlap, full != 0);
+  if (maxH <= 0) return false;
+  ilqc_model_desc md = *m;
+  md.horizon = maxH;
+  size_t off = 0;
+  c->solve = off; off += align_up(ilqc_solve_workspace_bytes(&md, a, B));
+  c->wcmd = off; off += align_up(sizeof(double) * (size_t)maxH * d.nu * B);
+  c->xfrozen = off; off += align_up(sizeof(double) * (size_t)d.nx * B);
+  c->traj = off; off += align_up(sizeof(double) * (size_t)(kMpcAdvanceChunk + 1) * d.nx * B);
+  c->step = off; off += align_up(sizeof(double) * (size_t)B);
+  c->met = off; off += align_up(sizeof(double) * (size_t)3 * (max_iter + 1) * B);
+  c->ints = off; off += align_up(sizeof(int32_t) * (size_t)2 * B);
+  c->total = off;
+  if (maxH_out) *maxH_out = maxH;
+  return true;
+}
+size_t ilqc_mpc_workspace_bytes(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, int full_horizon, int window_size,
+                                int overlap, int max_iter, int optim_on_full_window) {
+  MpcCarve c;
+  return mpc_carve(m, a, B, full_horizon, window_size, overlap, max_iter, optim_on_full_window, &c, nullptr) ? c.total : 0;
+}
+int ilqc_mpc(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const double* x0, int full_horizon, int window_size,
+             int overlap, int max_iter, int optim_on_full_window, int keep_applying_last_ctrl, int max_windows, double* cmd,
+             int32_t* cmd_len_host, double* cost, int32_t* status, int32_t* n_done, void* workspace, size_t workspace_bytes,
+             void* stream) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (!a || !x0 || !cmd || B <= 0 || m->pp_t0) return ILQC_E_ARG;
+  MpcCarve c;
+  int maxH = 0;
+  if (!mpc_carve(m, a, B, full_horizon, window_size, overlap, max_iter, optim_on_full_window, &c, &maxH)) return ILQC_E_ARG;
+  if (!workspace || workspace_bytes < c.total) return ILQC_E_WORKSPACE;
+  stream_t st = (stream_t)stream;
+  char* base = (char*)workspace;
+  double* wcmd = (double*)(base + c.wcmd);
+  double* xfrozen = (double*)(base + c.xfrozen);
+  double* trajs = (double*)(base + c.traj);
+  double* step = (double*)(base + c.step);
+  double* met = (double*)(base + c.met);
+  int32_t* ints = (int32_t*)(base + c.ints);
+  const size_t row = (size_t)d.nu * B, mrows = (size_t)(max_iter + 1) * B;
+  const bool full = optim_on_full_window != 0;
+  const bool regstep = a->algo_type != ILQC_ALGO_GD && (a->step_mode == ILQC_STEP_REG || a->step_mode == ILQC_STEP_REGVAR);
+  const double step0 = regstep ? 100.0 : 1.0;  // run_min_algo's default first stepsize (run_min_algo.py:59)
+#define ILQC_CHECK(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+  int curr = 0, k_frozen = 0, n_win = 0;
+  const double* xf = x0;  // state after the first k_frozen controls of cmd
+  for (int h = 0; h < full_horizon;) {
+    h = mpc_next_horizon(h, window_size, overlap, full_horizon);
+    ilqc_model_desc md = *m;
+    const double* xw = x0;
+    MpcWindow w;
+    if (curr == 0) {  // first window: run_min_algo(env, max_iter, algo) on env.horizon zeros
+      w.Hw = m->horizon; w.keep = 0; w.a = 0;
+      ILQC_CHECK(dev_memset(wcmd, 0, sizeof(double) * (size_t)w.Hw * row, st));
+    } else {
+      if (!mpc_window(curr, h, overlap, full, &w)) return ILQC_E_ARG;
+      // warm start: tail of the previous controls, then copies of the last control (or zeros)
+      if (w.n_tail > 0) ILQC_CHECK(dev_d2d(wcmd, cmd + (size_t)w.tail_start * row, sizeof(double) * (size_t)w.n_tail * row, st));
+      if (w.extra > 0) {
+        const int n = w.extra * (int)row;
+        ILQC_LAUNCH((mpc_pad_kernel), n, 256, st, n, (int)row, cmd + (size_t)(curr - 1) * row, wcmd + (size_t)w.n_tail * row, keep_applying_last_ctrl);
+      }
+      if (!full) {
+        // re-anchor: state after a_pos controls of the previous solution (the plant is the model)
+        if (w.a_pos < k_frozen) { k_frozen = 0; xf = x0; }
+        while (k_frozen < w.a_pos) {
+          const int n = w.a_pos - k_frozen < kMpcAdvanceChunk ? w.a_pos - k_frozen : (int)kMpcAdvanceChunk;
+          ilqc_model_desc ma = *m;
+          ma.horizon = n; ma.t0 = k_frozen;
+          ILQC_FOR_MODEL(effective_model(ma), ILQC_CHECK(LM::forward(0, ma, B, B, nullptr, xf, cmd + (size_t)k_frozen * row, nullptr, trajs, nullptr, nullptr, nullptr, st)));
+          ILQC_CHECK(dev_d2d(xfrozen, trajs + (size_t)n * d.nx * B, sizeof(double) * (size_t)d.nx * B, st));
+          xf = xfrozen;
+          k_frozen += n;
+        }
+        xw = xf;
+        md.t0 = w.a;
+      } else {
+        md.t0 = m->t0;
+      }
+    }
+    md.horizon = w.Hw;
+    ILQC_LAUNCH((fill_kernel), B, 256, st, B, step, step0);
+    double* cost_w = cost ? cost + (size_t)n_win * mrows : met;
+    int32_t* status_w = status ? status + (size_t)n_win * B : ints;
+    int32_t* n_done_w = n_done ? n_done + (size_t)n_win * B : ints + B;
+    ILQC_CHECK(solve_dispatch(&md, a, B, xw, wcmd, step, max_iter, cost_w, met + mrows, met + 2 * mrows, n_done_w, status_w,
+                              nullptr, base + c.solve, c.wcmd - c.solve, st));
+    // cmd_opt = prev_cmd[:-overlap] ++ cmd
+    ILQC_CHECK(dev_d2d(cmd + (size_t)w.keep * row, wcmd, sizeof(double) * (size_t)w.Hw * row, st));
+    curr = w.keep + w.Hw;
+    ++n_win;
+    if (max_windows > 0 && n_win >= max_windows) break;
+  }
+  ILQC_CHECK(dev_sync(st));
+#undef ILQC_CHECK
+  if (cmd_len_host) *cmd_len_host = curr;
+  return ILQC_LAUNCH_OK();
 }
 
 }  // extern "C"

@@ -165,6 +165,24 @@ ILQC_HD void cnorm_body(int b, int B, int H, const double* __restrict__ gsq, dou
   cnorm[b] = ::sqrt(s);
 }
 
+// norm that scales the regularised line search, from a stored packed expansion (algos_steps.py:342-351):
+// sqrt(sum_{t>=1} |grad_ctrl_t|^2 + |grad_state_t|^2), summed in time order like forward_body does
+template <class M>
+ILQC_HD void cnorm_lin_body(const ilqc_model_desc& m, int b, int B, const double* __restrict__ lin, double* __restrict__ cnorm) {
+  using L = Layout<M>;
+  double gsum = 0.0;
+  for (int t = 0; t < m.horizon; ++t) {
+    const double* rec = lin + (size_t)t * L::stride * B + b;
+    double gc = 0.0, gs = 0.0;
+#pragma unroll
+    for (int i = 0; i < M::NU; ++i) { const double v = rec[(size_t)(L::oq + i) * B]; gc += v * v; }
+#pragma unroll
+    for (int i = 0; i < L::np; ++i) { const double v = rec[(size_t)(L::op + i) * B]; gs += v * v; }
+    gsum += gc + gs;
+  }
+  cnorm[b] = ::sqrt(gsum);
+}
+
 // ----------------------------------------------------------------------------------------------------
 // loads of the packed record into the Riccati operands.  `rd(slot)` returns entry `slot` of the record.
 // ----------------------------------------------------------------------------------------------------

@@ -56,10 +56,12 @@ inline long long& launch_counter() { static long long n = 0; return n; }
 #define ILQC_LAUNCH_SMEM(kern, n, block, smem, stream, ...)                                                   \
   do {                                                                                                         \
     if ((n) > 0) {                                                                                             \
-      static bool _attr_set = false;                                                                           \
-      if (!_attr_set && (smem) > 0) {                                                                          \
+      static bool _attr_set[64] = {};  /* the attribute is per device */                                      \
+      int _dev = 0;                                                                                            \
+      cudaGetDevice(&_dev);                                                                                    \
+      if ((smem) > 0 && !_attr_set[_dev & 63]) {                                                               \
         cudaFuncSetAttribute(ILQC_UNPAREN kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem));     \
-        _attr_set = true;                                                                                      \
+        _attr_set[_dev & 63] = true;                                                                           \
       }                                                                                                        \
       ILQC_UNPAREN kern<<<((n) + (block)-1) / (block), (block), (smem), (stream)>>>(__VA_ARGS__);               \
       ++::ilqc::launch_counter();                                                                              \
@@ -126,6 +128,7 @@ struct Launch {
                      stream_t st);
   static int adjoint(const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob, const double* lin,
                      double* grad, double* gnorm, stream_t st);
+  static int cnorm_lin(const ilqc_model_desc& m, int B, const double* lin, double* cnorm, stream_t st);
   static void dims(int* nx, int* nu, int* lin_stride, int* gain_stride, int* hess_stride);
 };
 

@@ -108,6 +108,12 @@ ILQC_GLOBAL_LB(ILQC_LB_BWD) hess_kernel(ilqc_model_desc m, int B, int n_probs, c
 }
 
 template <class M>
+ILQC_GLOBAL cnorm_lin_kernel(ilqc_model_desc m, int B, const double* lin, double* cnorm) {
+  const int b = ILQC_TID;
+  if (b < B) cnorm_lin_body<M>(m, b, B, lin, cnorm);
+}
+
+template <class M>
 ILQC_GLOBAL adjoint_kernel(ilqc_model_desc m, int B, int n_threads, const int32_t* prob, const double* lin,
                            double* grad, double* gnorm) {
   const int a = ILQC_TID;
@@ -315,6 +321,12 @@ template <>
 int Launch<ILQC_MODEL_INST>::adjoint(const ilqc_model_desc& m, int B, int n_threads, const int32_t* prob,
                                      const double* lin, double* grad, double* gnorm, stream_t st) {
   ILQC_LAUNCH((adjoint_kernel<MI>), n_threads, kBlock, st, m, B, n_threads, prob, lin, grad, gnorm);
+  return ILQC_LAUNCH_OK();
+}
+
+template <>
+int Launch<ILQC_MODEL_INST>::cnorm_lin(const ilqc_model_desc& m, int B, const double* lin, double* cnorm, stream_t st) {
+  ILQC_LAUNCH((cnorm_lin_kernel<MI>), B, 256, st, m, B, lin, cnorm);
   return ILQC_LAUNCH_OK();
 }
 

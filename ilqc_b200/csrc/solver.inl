@@ -293,6 +293,10 @@ ILQC_GLOBAL ls_select_kernel(LsParams P, int n_active, int B, int n_slots, const
     } else {
       status[b] = ILQC_NO_DIRECTION;  // min_step returns None (algos_steps.py:379-380)
       curr_val[b] = NAN;
+      if (P.line_search) {  // ... with the last trial step (rescaled in 'reg' mode, algos_steps.py:372-373)
+        const double s = step_true[slot];
+        stepsize[b] = (P.step_mode == ILQC_STEP_REG && P.algo_type != ILQC_ALGO_GD) ? s * cnorm[b] : s;
+      }
       if (A.phase) {
         const int it = A.iter[b];
         if (A.ls_trips) A.ls_trips[(size_t)it * B + b] = ntrip;
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(1024) plan_async_kernel(int B, const int32_t* 
 // at its own iteration index, followed by the line-search set-up of its next iteration (ls_init_kernel)
 ILQC_GLOBAL status_async_kernel(LsParams P, int n_list, const int32_t* list, int B, int n_iter, const double* curr_val,
                                 const double* gnorm, const double* cnorm, const double* stepsize, double* s_try,
-                                double* dec_unit, int32_t* trips, int32_t* status, AsyncState A) {
+                                double* dec_unit, int32_t* trips, int32_t* status, AsyncState A, const double* cost0) {
   const int a = ILQC_TID;
   if (a >= n_list) return;
   const int b = list[a];
@@ -455,7 +459,7 @@ ILQC_GLOBAL status_async_kernel(LsParams P, int n_list, const int32_t* list, int
   A.step_rep[row] = srep;
   A.n_done[b] = it;
   int st = ILQC_RUNNING;
-  const double c0 = A.cost[b];
+  const double c0 = cost0 ? cost0[b] : A.cost[b];
   if (c != c || c > c0 + 1e3) st = ILQC_DIVERGED;
   if (it > 0) {
     const double cp = A.cost[(size_t)(it - 1) * B + b];
@@ -494,7 +498,7 @@ ILQC_GLOBAL apply_kernel(int n_active, int n_elem, int B, int n_slots, const int
 // collect_info + check_cvg_status (run_min_algo.py:127-264) for metrics row `it`
 ILQC_GLOBAL status_kernel(LsParams P, int B, int it, const double* curr_val, const double* gnorm,
                           const double* stepsize, double* cost, double* gn, double* step_rep, int32_t* status,
-                          int32_t* n_done) {
+                          int32_t* n_done, const double* cost0) {
   const int b = ILQC_TID;
   if (b >= B) return;
   const size_t row = (size_t)it * B + b;
@@ -516,7 +520,7 @@ ILQC_GLOBAL status_kernel(LsParams P, int B, int it, const double* curr_val, con
   step_rep[row] = srep;
   n_done[b] = it;
   int st = ILQC_RUNNING;
-  const double c0 = cost[b];
+  const double c0 = cost0 ? cost0[b] : cost[b];  // (restart: the original metrics['cost'][0], ilqc_algo_desc.pp_cost0)
   if (c != c || c > c0 + 1e3) st = ILQC_DIVERGED;
   if (it > 0) {
     const double cp = cost[(size_t)(it - 1) * B + b];
@@ -588,10 +592,12 @@ inline int wave_slots() {
 #if defined(ILQC_HOSTSIM)
   return 4096;
 #else
-  static int cached = 0;
+  static int cached_by_dev[64] = {};  // (SM count of the CURRENT device: engines on several GPUs share this code)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& cached = cached_by_dev[dev & 63];
   if (!cached) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
+    int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cached = sms * ILQC_WAVE_THREADS_PER_SM;
     if (const char* e = getenv("ILQC_WAVE_SLOTS")) {  // tuning knob (tools/gpu_tune.sh)
@@ -715,6 +721,8 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
   ILQC_LAUNCH((fill_i32_kernel), B, 256, st, B, n_done, (int32_t)0);
   ILQC_LAUNCH((fill_i32_kernel), B, 256, st, B, w.feas_prob, (int32_t)1);
   ILQC_LAUNCH((fill_kernel), B, 256, st, B, w.gnorm, (double)NAN);
+  // (rows of iterations that never run - every problem stopped early - report 0 trips, like the asynchronous driver)
+  if (ls_trips && n_iter > 0) ILQC_LAUNCH((fill_i32_kernel), n_iter * B, 256, st, n_iter * B, ls_trips, (int32_t)0);
 
   // iteration 0: objective of the initial controls (same arithmetic as every candidate evaluation), its
   // expansion and the metrics row 0 (run_min_algo.py:65-76)
@@ -724,7 +732,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
   if (quad) ILQC_PROF(PROF_LINEARIZE, 0, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, B, nullptr, w.traj, cmd, w.hess, st))));
   if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
   ILQC_LAUNCH((status_kernel), B, 256, st, P, B, 0, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
-              n_done);
+              n_done, a->pp_cost0);
 
   for (int it = 1; it <= n_iter; ++it) {
     ILQC_LAUNCH((ls_init_kernel), B, 256, st, P, B, status, stepsize, w.cnorm, w.s_try, w.flags, w.trips);
@@ -734,7 +742,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
     if (n_active == 0) {
       for (int r = it; r <= n_iter; ++r)
         ILQC_LAUNCH((status_kernel), B, 256, st, P, B, r, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep,
-                    status, n_done);
+                    status, n_done, a->pp_cost0);
       break;
     }
     if (a->algo_type == ILQC_ALGO_GD) {
@@ -804,7 +812,7 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
   if (quad) ILQC_PROF(PROF_LINEARIZE, 0, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, B, nullptr, w.traj, cmd, w.hess, st))));
     if (need_grad) ILQC_PROF(PROF_ADJOINT, B, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, B, nullptr, w.lin, w.dir, w.gnorm, st))));
     ILQC_LAUNCH((status_kernel), B, 256, st, P, B, it, w.curr_val, w.gnorm, stepsize, cost, gnorm_out, step_rep, status,
-                n_done);
+                n_done, a->pp_cost0);
   }
   ILQC_CHECK(dev_sync(st));
   prof.flush();

@@ -82,6 +82,7 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
   // stragglers allowed to lag behind the bulk: ~2 % of the batch, at least one block's worth
   int lag = B / 50 < 64 ? 64 : B / 50;
   if (const char* e = getenv("ILQC_LAG")) lag = atoi(e);  // tuning knob
+  if (lag < 0) lag = 0;
   const int n_rows = (n_iter + 1) * B;
   ILQC_LAUNCH((fill_i32_kernel), B, 256, st, B, status, (int32_t)ILQC_RUNNING);
   ILQC_LAUNCH((fill_i32_kernel), B, 256, st, B, n_done, (int32_t)0);
@@ -108,7 +109,7 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
     // stream A while stream B re-expands the bulk, and join the bulk's next rounds with their own (wider)
     // candidate counts, one iteration behind.  The lock-step driver instead spends 2 latency-bound rounds per
     // iteration on them with the rest of the GPU idle.
-    const bool do_lin = n_lin > 0 && n_ls <= lag;
+    const bool do_lin = n_lin > 0 && (n_ls <= lag || n_ls == 0);
     if (trace_rounds()) fprintf(stderr, "ilqc tick: t %.3f ms ls %d lin %d slots %d do_lin %d\n", trace_ms(), n_ls, n_lin, n_slots, (int)do_lin);
 #if !defined(ILQC_HOSTSIM)
     cudaEventRecord(ss.ev_a, st);
@@ -120,7 +121,7 @@ inline int solve_async_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, i
       if (quad) ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::hess(md, B, n_lin, w.ident, w.traj, cmd, w.hess, sb)));
       if (need_grad) ILQC_PROF_ON(sb, PROF_ADJOINT, n_lin, ILQC_FOR_MODEL(effective_model(md), ILQC_CHECK(LM::adjoint(md, B, n_lin, w.ident, w.lin, w.dir, w.gnorm, sb))));
       ILQC_LAUNCH((status_async_kernel), n_lin, 256, sb, P, n_lin, w.ident, B, n_iter, w.curr_val, w.gnorm, w.cnorm, stepsize,
-                  w.s_try, w.dec_unit, w.trips, status, A);
+                  w.s_try, w.dec_unit, w.trips, status, A, a->pp_cost0);
     }
     // ---- stream A: line-search candidates of the LS problems ----
     // (ILQC_DEFER=1: the stragglers skip the re-expansion tick and continue inside the bulk's next big launch)

@@ -272,7 +272,7 @@ class Engine:
 
     # ---- run_min_algo -------------------------------------------------------------------------------------
     def algo_desc(self, algo, n_candidates=1, line_search=True, compute_grad_norm=True, max_ls_trips=0, scheduler=0,
-                  handle_bad_dir="check_total_value", expansion=0):
+                  handle_bad_dir="check_total_value", expansion=0, cost0=None):
         a = _lib.AlgoDesc()
         a.algo_type, a.approx, a.step_mode = parse_algo(algo)
         a.n_candidates = int(n_candidates)
@@ -284,6 +284,8 @@ class Engine:
             raise NotImplementedError(handle_bad_dir)
         a.handle_bad_dir = _lib.BAD_DIR[handle_bad_dir]
         a.expansion = int(expansion)
+        if cost0 is not None:      # restart: the original metrics['cost'][0] per problem (kept alive by the caller)
+            a.pp_cost0 = cost0.data_ptr()
         return a
 
     def workspace(self, nbytes):
@@ -294,8 +296,10 @@ class Engine:
 
     def solve(self, env, algo="ddp_linquad_reg", max_iter=10, x0=None, cmd0=None, stepsize=None, batch=None,
               weights=None, t0=None, horizon=None, n_candidates=128, line_search=True, compute_grad_norm=True,
-              record_trips=False, max_ls_trips=0, scheduler=0, handle_bad_dir="check_total_value", expansion=0):
-        """run_min_algo for a batch of problems of one family (device tensors in / out)."""
+              record_trips=False, max_ls_trips=0, scheduler=0, handle_bad_dir="check_total_value", expansion=0,
+              cost0=None):
+        """run_min_algo for a batch of problems of one family (device tensors in / out).  cost0 [B]: the first cost
+        of an earlier call this one continues (restart, run_min_algo(past_metrics=...))."""
         if cmd0 is not None:
             cmd0 = self._dev(cmd0)
             B, H, nu = cmd0.shape
@@ -305,7 +309,9 @@ class Engine:
         x0 = self._x0(env, x0, B).reshape(B, -1)
         d, keep = self.make_desc(env, H, B, t0, weights)
         nx, nu = self.dims(d)
-        a = self.algo_desc(algo, n_candidates, line_search, compute_grad_norm, max_ls_trips, scheduler, handle_bad_dir, expansion)
+        cost0 = None if cost0 is None else self._dev(cost0).reshape(B)
+        a = self.algo_desc(algo, n_candidates, line_search, compute_grad_norm, max_ls_trips, scheduler, handle_bad_dir, expansion,
+                           cost0)
         cmds = self.to_soa(cmd0) if cmd0 is not None else torch.zeros(H * nu, B, dtype=F64, device=self.device)
         if stepsize is None:
             stepsize = default_stepsize(algo)
@@ -352,6 +358,38 @@ class Engine:
                                             C.c_size_t(nbytes), self._stream()), "ilqc_solve_host")
         return SolveResult(cmd=cmd_host, stepsize=stepsize_host, cost=cost, norm_grad_obj=gnorm,
                            stepsize_reported=srep, n_done=n_done, status=status)
+
+    def mpc(self, env, x0, full_horizon, window_size, overlap, max_iter=10, algo="ddp_linquad_reg", weights=None,
+            n_candidates=128, optim_on_full_window=False, keep_applying_last_ctrl=True, max_windows=0, expansion=0):
+        """ilqc_mpc: B concurrent closed-loop episodes (run_mpc, mpc_pipeline.py:87-115), window loop inside the call.
+        Returns (cmd [B,T,nu], cost [B,W,max_iter+1], status [B,W], n_done [B,W])."""
+        x0 = self._dev(x0)
+        B = x0.shape[0]
+        d, keep = self.make_desc(env, env.horizon, B, env.init_time_iter, weights)
+        nx, nu = self.dims(d)
+        a = self.algo_desc(algo, n_candidates, True, True, 0, 0, "check_total_value", expansion)
+        W = self.lib.ilqc_mpc_num_windows(int(full_horizon), int(window_size), int(overlap))
+        if W <= 0:
+            raise _lib.IlqcError("ilqc_mpc_num_windows: invalid window geometry")
+        if max_windows:
+            W = min(W, int(max_windows))
+        nbytes = self.lib.ilqc_mpc_workspace_bytes(C.byref(d), C.byref(a), B, int(full_horizon), int(window_size), int(overlap),
+                                                   int(max_iter), int(bool(optim_on_full_window)))
+        if nbytes == 0:
+            raise _lib.IlqcError("ilqc_mpc_workspace_bytes: invalid arguments")
+        ws = self.workspace(nbytes)
+        x0s = self.to_soa(x0)
+        cmd = torch.zeros(int(full_horizon) * nu, B, dtype=F64, device=self.device)
+        cost = self.empty(W, max_iter + 1, B)
+        status, n_done = self.empty(W, B, dtype=torch.int32), self.empty(W, B, dtype=torch.int32)
+        n_rows = C.c_int32(0)
+        _lib.check(self.lib.ilqc_mpc(C.byref(d), C.byref(a), B, self._ptr(x0s), int(full_horizon), int(window_size), int(overlap),
+                                     int(max_iter), int(bool(optim_on_full_window)), int(bool(keep_applying_last_ctrl)),
+                                     int(max_windows or 0), self._ptr(cmd), C.byref(n_rows), self._ptr(cost), self._ptr(status),
+                                     self._ptr(n_done), self._ptr(ws), C.c_size_t(nbytes), self._stream()), "ilqc_mpc")
+        T = n_rows.value
+        return (self.from_soa(cmd[:T * nu], B, T, nu), cost.permute(2, 0, 1).contiguous(), status.t().contiguous(),
+                n_done.t().contiguous())
 
     def fastmath_eval(self, fn, a, b=None):
         """Self-test of csrc/fastmath.cuh: fn in {sincos, atan2, atan, div, rcp, sqrt_rsqrt}, elementwise."""

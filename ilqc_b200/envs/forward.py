@@ -88,7 +88,9 @@ class DiffEnv:
         if approx is None:
             tr, ct, _ = eng.rollout_cost(self, x0, cmd_t.reshape(1, H, -1), t0=time_iter)
             tr, ct = tr[0].cpu(), ct[0].cpu()
-            return [tr[t] for t in range(H + 1)], [ct[t] for t in range(H + 1)]
+            traj, costs = [tr[t] for t in range(H + 1)], [ct[t] for t in range(H + 1)]
+            traj[0]._ilqc = costs[0]._ilqc = dict(env=self, x0=x0, cmd=cmd_t, t0=time_iter, approx=None)
+            return traj, costs
         if approx not in ("linquad", "quad"):
             raise NotImplementedError(approx)
         ex = eng.expand_dense(self, x0, cmd_t.reshape(1, H, -1), t0=time_iter)
@@ -120,7 +122,7 @@ class DiffEnv:
                 traj[t + 1].hess_dyn_state_ctrl = (lambda lam, h=h: h(lam)[1])
                 traj[t + 1].hess_dyn_ctrl = (lambda lam, h=h: h(lam)[2])
         # what the batched kernels need to redo the expansion on the device
-        traj[0]._ilqc = dict(env=self, x0=x0, cmd=cmd_t, t0=time_iter, approx=approx)
+        traj[0]._ilqc = costs[0]._ilqc = dict(env=self, x0=x0, cmd=cmd_t, t0=time_iter, approx=approx)
         return traj, costs
 
     def close(self):

@@ -1,1 +1,1 @@
-from .fhc_pipeline import solve_ctrl_pb
+from .fhc_pipeline import solve_ctrl_pb, solve_ctrl_pb_incrementally, check_exp_done

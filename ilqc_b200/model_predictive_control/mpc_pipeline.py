@@ -14,7 +14,7 @@ from typing import Any, Optional
 
 import torch
 
-from ..algorithms.run_min_algo import run_min_algo, run_min_algo_batched
+from ..algorithms.run_min_algo import run_min_algo, run_min_algo_batched, check_cvg_status
 from ..engine import default_engine
 from ..envs import make_env
 
@@ -53,6 +53,33 @@ def run_mpc_step(env_cfg: dict[str, Any], optim_cfg: dict[str, Any], prev_cmd: O
     return dict(cmd_opt=cmd_opt, metrics=metrics)
 
 
+def check_exp_fail(exp_outputs: dict[str, Any]) -> bool:
+    return check_cvg_status(exp_outputs["metrics"], verbose=False) == "diverged"
+
+
+def run_mpc(env_cfg: dict[str, Any], optim_cfg: dict[str, Any]) -> torch.Tensor:
+    """run_mpc of the reference (mpc_pipeline.py:87-115) for one episode: windows of growing `full_horizon`, each
+    warm-started from the previous window's cmd_opt, stop at the first diverged window.  The chain is carried in memory
+    (the reference stores every window in its on-disk experiment cache, utils_pipeline/).  For many concurrent episodes
+    use run_mpc_batched / the C entry ilqc_mpc."""
+    from copy import deepcopy
+    horizon = 0
+    max_horizon, window_size, overlap = optim_cfg["full_horizon"], optim_cfg["window_size"], optim_cfg["overlap"]
+    sliding_time = window_size - overlap
+    exp_outputs, prev = None, None
+    while horizon < max_horizon:
+        temp_optim_cfg = deepcopy(optim_cfg)
+        horizon = min(max(horizon + sliding_time, window_size), max_horizon)
+        del temp_optim_cfg["window_size"]
+        temp_optim_cfg["full_horizon"] = horizon
+        exp_outputs = run_mpc_step(env_cfg, temp_optim_cfg, prev_cmd=prev)
+        prev = exp_outputs["cmd_opt"]
+        if check_exp_fail(exp_outputs):
+            print("Maximum horizon: {}".format(horizon))
+            break
+    return exp_outputs["cmd_opt"]
+
+
 @dataclass
 class MpcResult:
     cmd: torch.Tensor        # [B, full_horizon, nu] applied + planned controls (cmd_opt of the last window)
@@ -79,46 +106,18 @@ def run_mpc_batched(env, full_horizon: int, window_size: int, overlap: int, max_
     x0 = torch.as_tensor(x0, dtype=torch.float64).to(dev)
     B = x0.shape[0]
     wts = None if weights is None else torch.as_tensor(weights, dtype=torch.float64).to(dev)
-    sliding = window_size - overlap
     if expansion is None:
         # windows of a few thousand episodes do not fill the GPU: expand every time step of every episode at once
         # (ilqc_algo_desc.expansion = 1) instead of walking each window's horizon in one thread
         expansion = 1 if B <= 8192 else 0
-    horizon, costs, stats, horizons, n_it = 0, [], [], [], 0
-    cmd_hist = None                      # [B, T, nu]
-    k_frozen, x_frozen = 0, x0           # state after the first k_frozen controls of cmd_hist
-    while horizon < full_horizon:
-        horizon = min(max(horizon + sliding, window_size), full_horizon)
-        if cmd_hist is None:
-            r = run_min_algo_batched(env, max_iter, algo, x0=x0, weights=wts, t0=0, n_candidates=n_candidates, engine=eng,
-                                     expansion=expansion)
-            cmd_hist = r.cmd
-        else:
-            curr = cmd_hist.shape[1]
-            extra = horizon - curr
-            pad = cmd_hist[:, -1:].repeat(1, extra, 1) if keep_applying_last_ctrl else cmd_hist.new_zeros(B, extra, cmd_hist.shape[2])
-            if optim_on_full_window:
-                # the env keeps its initial state and time (mpc_pipeline.py:35-36); the window is the whole horizon
-                r = run_min_algo_batched(env, max_iter, algo, x0=x0, prev_cmd=torch.cat((cmd_hist, pad), dim=1), weights=wts,
-                                         t0=0, n_candidates=n_candidates, engine=eng, expansion=expansion)
-                cmd_hist = r.cmd
-            else:
-                init_cmd = torch.cat((cmd_hist[:, curr - overlap:], pad), dim=1)
-                a = curr - overlap       # anchor index into the trajectory of cmd_hist (may be negative: Python slicing)
-                a_pos = a if a >= 0 else curr + 1 + a
-                if a_pos < k_frozen:
-                    k_frozen, x_frozen = 0, x0
-                if a_pos > k_frozen:     # advance the frozen prefix with the plant = model
-                    traj, _, _ = eng.rollout_cost(env, x_frozen, cmd_hist[:, k_frozen:a_pos], t0=k_frozen, weights=wts)
-                    x_frozen, k_frozen = traj[:, -1].contiguous(), a_pos
-                r = run_min_algo_batched(env, max_iter, algo, x0=x_frozen, prev_cmd=init_cmd, weights=wts, t0=a,
-                                         n_candidates=n_candidates, engine=eng, expansion=expansion)
-                cmd_hist = torch.cat((cmd_hist[:, :-overlap], r.cmd), dim=1)  # prev_cmd[:-overlap] (mpc_pipeline.py:53)
-        costs.append(r.cost)
-        stats.append(r.status)
-        horizons.append(horizon)
-        n_it += int(r.n_done.sum().item())
-        if max_windows is not None and len(horizons) >= max_windows:
-            break
-    return MpcResult(cmd=cmd_hist, cost=torch.stack(costs, dim=1), status=torch.stack(stats, dim=1),
-                     horizons=horizons, n_iterations=n_it)
+    # the window loop, the warm-start shift and the re-anchoring run inside ilqc_mpc (csrc/mpc.inl)
+    cmd, cost, status, n_done = eng.mpc(env, x0, full_horizon, window_size, overlap, max_iter, algo, weights=wts,
+                                        n_candidates=n_candidates, optim_on_full_window=optim_on_full_window,
+                                        keep_applying_last_ctrl=keep_applying_last_ctrl, max_windows=max_windows or 0,
+                                        expansion=expansion)
+    horizons, h = [], 0
+    sliding = window_size - overlap
+    while h < full_horizon and len(horizons) < cost.shape[1]:
+        h = min(max(h + sliding, window_size), full_horizon)
+        horizons.append(h)
+    return MpcResult(cmd=cmd, cost=cost, status=status, horizons=horizons, n_iterations=int(n_done.sum().item()))

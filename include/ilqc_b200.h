@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ILQC_ABI_VERSION 1
+#define ILQC_ABI_VERSION 2
 
 enum { ILQC_E_ARG = -1, ILQC_E_UNSUPPORTED = -2, ILQC_E_WORKSPACE = -3 };
 
@@ -101,6 +101,10 @@ typedef struct ilqc_algo_desc {
                                large batches).  1: time-parallel, for small batches (MPC windows, single problems):
                                a roll-out pass stores the trajectory, then one thread per (problem, time step)
                                expands its step.  Same mathematics; the two modes differ by rounding (1e-14). */
+  int32_t reserved1, reserved2;
+  const double* pp_cost0;   /* [B] device, nullable.  Restart (run_min_algo(past_metrics=...), run_min_algo.py:72-75):
+                               the ORIGINAL metrics['cost'][0] of every problem, against which check_cost_status tests
+                               divergence (cost > cost[0] + 1e3, run_min_algo.py:240-243).  NULL: row 0 of this call. */
 } ilqc_algo_desc;
 
 int ilqc_abi_version(void);
@@ -133,7 +137,7 @@ int ilqc_expand_dense(const ilqc_model_desc* m, int B, const double* x0, const d
                       double* Hxx, double* Hxu, double* Huu, void* stream);
 
 /* lin_quad_backward (backward.py:6-57) / bell_step+bell_core (:153-257) on DENSE expansions of any small
- * size (nx<=8, nu<=4 instantiated): one thread per (problem, candidate).  n_slots = B*L, slot = b*L+c uses
+ * size (instantiated (nx, nu): (2,1) (4,1) (4,3) (4,4) (6,3) (8,3); other sizes return ILQC_E_UNSUPPORTED): one thread per (problem, candidate).  n_slots = B*L, slot = b*L+c uses
  * problem b and reg_ctrl[slot].  R is nullable ([H][nx][nu][B], quad_backward's cross term).
  * out K [H][nu][nx][n_slots], k [H][nu][n_slots], jcst [n_slots]. */
 int ilqc_lq_backward_dense(int nx, int nu, int H, int B, int L, const double* A, const double* Bm,
@@ -164,7 +168,7 @@ int ilqc_rollout(const ilqc_model_desc* m, int kind, int B, int n_slots, const i
 /* grad_u sum(costs) through the adjoint recursion on the packed expansion (replaces
  * torch.autograd.grad(sum(costs), cmd), run_min_algo.py:157, algos_steps.py:37) and the norm used to
  * scale the regularised line search (algos_steps.py:342-351).
- * out grad [H][nu][B] (nullable), gnorm [B] = ||grad||, cnorm [B] = sqrt(sum |grad_ctrl|^2+|grad_state|^2). */
+ * out grad [H][nu][B] (nullable), gnorm [B] = ||grad||, cnorm [B] (nullable) = sqrt(sum_t |grad_ctrl_t|^2+|grad_state_t|^2). */
 int ilqc_grad_obj(const ilqc_model_desc* m, int B, const double* lin, double* grad, double* gnorm,
                   double* cnorm, void* stream);
 
@@ -172,7 +176,6 @@ int ilqc_grad_obj(const ilqc_model_desc* m, int B, const double* lin, double* gr
  * cmd [H][nu][B] in/out, stepsize [B] in/out (the optimiser's auxiliary variable),
  * metrics out: cost/gnorm/step_rep [n_iter+1][B] (NaN-padded after a problem stops), n_done [B] iterations
  * executed, status [B]; ls_trips [n_iter][B] (nullable) line-search trips per iteration.
- * first_iter: index of the first metrics row to fill (0 = also evaluate the initial point).
  * workspace: device scratch of at least ilqc_solve_workspace_bytes(). Synchronises the stream (it reads
  * back the number of problems still searching after every line-search round). */
 size_t ilqc_solve_workspace_bytes(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B);
@@ -190,6 +193,27 @@ int ilqc_solve_host(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, co
                     double* gnorm_host, double* step_rep_host, int32_t* n_done_host, int32_t* status_host,
                     void* workspace, size_t workspace_bytes, void* stream);
 size_t ilqc_solve_host_workspace_bytes(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, int n_iter);
+
+/* run_mpc (model_predictive_control/mpc_pipeline.py:87-115) for B concurrent closed-loop episodes, the plant being
+ * the model: windows of growing full_horizon h <- min(max(h + window_size - overlap, window_size), full_horizon),
+ * every window = mpc_step (mpc_pipeline.py:18-55): warm start from the last `overlap` controls of the previous
+ * window + (full_horizon - previous length) copies of its last control (or zeros, keep_applying_last_ctrl = 0),
+ * initial state re-anchored on the trajectory of the previous controls (Python's negative-index behaviour
+ * included when the previous window is shorter than the overlap), init_time_iter = previous length - overlap,
+ * result spliced behind the frozen prefix.  optim_on_full_window = 1 re-optimises the whole horizon from x0.
+ * The first window is solved on m->horizon steps (run_min_algo sizes cmd from env.horizon, run_min_algo.py:53).
+ * The window loop, the warm-start shift / padding kernel and the re-anchoring roll-out run inside this call:
+ * no per-window host work besides the launches.
+ * x0 [nx][B]; out cmd [full_horizon][nu][B] (rows >= the last window's horizon untouched), cmd_len (host int,
+ * number of valid rows); per-window metrics (nullable): cost [W][max_iter+1][B], status [W][B], n_done [W][B]
+ * with W = ilqc_mpc_num_windows(...), or max_windows if 0 < max_windows < W.  m->pp_t0 must be NULL. */
+int ilqc_mpc_num_windows(int full_horizon, int window_size, int overlap);
+size_t ilqc_mpc_workspace_bytes(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, int full_horizon,
+                                int window_size, int overlap, int max_iter, int optim_on_full_window);
+int ilqc_mpc(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const double* x0, int full_horizon,
+             int window_size, int overlap, int max_iter, int optim_on_full_window, int keep_applying_last_ctrl,
+             int max_windows, double* cmd, int32_t* cmd_len_host, double* cost, int32_t* status, int32_t* n_done,
+             void* workspace, size_t workspace_bytes, void* stream);
 
 /* [B][R][C] (reference layout, batch outermost) <-> [R][C][B] (engine layout) on the device. */
 int ilqc_to_soa(const double* src, double* dst, int B, int n, void* stream);

@@ -21,7 +21,7 @@ CHAOTIC = {
 def test_cuda_library_loaded(cuda_engine):
     from ilqc_b200 import _lib
     assert cuda_engine.device.type == "cuda"
-    assert cuda_engine.lib.ilqc_abi_version() == 1
+    assert cuda_engine.lib.ilqc_abi_version() == _lib.ABI_VERSION
     assert not hasattr(cuda_engine.lib, "ilqc_is_hostsim_marker")
     assert _lib.CUDA_LIB_PATH.endswith("libilqc_b200.so")
 

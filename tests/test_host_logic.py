@@ -26,7 +26,7 @@ def test_cabi_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), name
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
-    assert _lib.bind(path).ilqc_abi_version() == 1
+    assert _lib.bind(path).ilqc_abi_version() == _lib.ABI_VERSION
 
 
 def test_product_has_no_cpu_fallback():
