@@ -2,7 +2,8 @@
 """Benchmark of the batched iLQR/DDP hot path (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
-    python bench.py --impl reference --gpus N --steps K ...   # CPU reference arm (oracle port, host cores)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU reference arm (the unmodified reference from
+                                                              # oracle/_ref, else the oracle port; host cores)
 
 Workload (config.workload): BASELINE.json configs[3] per-GPU slice = bicycle (Pacejka) car on the simple
 track, contouring cost, RK4 constant-control, H=100, dt=0.01, `ddp_linquad_reg` (the algorithm the metric /
@@ -21,11 +22,6 @@ import subprocess
 import sys
 import threading
 import time
-
-# stdout carries exactly one JSON line: NCCL's version banner / debug log go to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # (that level printf()s its banner to stdout)
-    os.environ["NCCL_DEBUG"] = "WARN"
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -47,14 +43,20 @@ FLOPS_PER_STEP = {  # kernel class -> algorithmic flops per (slot, time step)
     "adjoint": 2 * (NX * NX + NX * NU),      # adjoint_kernel
 }
 CLASSES = ["rollout_cost", "linearize", "backward", "rollout_candidate", "adjoint"]
-# EXECUTED FP64 flops per (slot, time step) = dadd + dmul + 2 dfma thread instructions counted by ncu
-# (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on, profiles/r01_ncu_hot_kernels_v3.txt).  The convention
-# above counts a transcendental or a division as ONE flop (each is 10-40 FP64 instructions) and the Riccati step
-# as dense 8x8 algebra (the kernel skips the structural zeros), so both views are reported.
-EXEC_FLOPS_PER_STEP = {"rollout_cost": 2000, "linearize": 4604, "backward": 1495, "rollout_candidate": 2115, "adjoint": 176}
-# DRAM bytes per slot per launch of the same ncu capture (dram__bytes_read.sum + dram__bytes_write.sum of a
-# 131072-slot launch = 4 candidates for each of 32768 problems; per-problem rows are shared by the candidates)
-NCU_DRAM_BYTES_PER_SLOT = {"rollout_candidate": 26350, "backward": 31900, "linearize": 50100}
+# EXECUTED FP64 flops per (slot, time step) (ncu: dadd + dmul + 2 dfma thread instructions) and DRAM bytes per slot per
+# launch (ncu: dram__bytes_read.sum + dram__bytes_write.sum of a 131072-slot launch) come from the LAST ncu capture,
+# profiles/kernel_counters.json (written by tools/ncu_counters.py, stamped with the commit it was taken at): they go
+# stale with a kernel edit, so the bench line names the capture it used.  The convention above counts a transcendental
+# or a division as ONE flop (each is 10-40 FP64 instructions) and the Riccati step as dense 8x8 algebra (the kernel
+# skips the structural zeros), so both views are reported.
+def load_counters():
+    try:
+        c = json.load(open(os.path.join(ROOT, "profiles", "kernel_counters.json")))
+        return c
+    except Exception:
+        return None
+
+
 LIN_STRIDE, GAIN_STRIDE = 52, 27
 BYTES_PER_SLOT = {  # algorithmic HBM bytes per slot per launch (H=100): reads + writes of the SoA arrays
     "rollout_cost": 8 * (NX + 100 * NU + 1),
@@ -145,29 +147,72 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU reference arm: the oracle port of the reference's algorithm on the host cores
+# CPU reference arm: the reference's own CPU implementation of the path on the host cores
+#   kind "reference": the UNMODIFIED reference (oracle/_ref, populated from /root/reference by oracle/make_ref.py)
+#   kind "port"     : oracle/ilqc_oracle.py (same torch ops) when oracle/_ref is absent
 # ------------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    seed, iters = args
+WORKLOAD = "bicycle car RK4 H=100 dt=0.01 contouring, ddp_linquad_reg (BASELINE configs[3], per-GPU slice)"
+CPU_ITERS = 3   # solver iterations per problem of one CPU sample (iteration 1 from cmd=0 needs 1.1 line-search trips, the
+#                 following ones 4-5 like the steady state: both rates are reported)
+
+
+def _cpu_impl():
+    from oracle import make_ref
+    if make_ref.ref_available():
+        R = make_ref.load_ref()
+        return "reference", R.make_env, R.run_min_algo
+    from oracle import ilqc_oracle as orc
+    return "port", orc.make_env, orc.run_min_algo
+
+
+def _cpu_warm(_):
+    """imports + one tiny solve in every worker process (kept out of the timed sample)"""
     import torch
     torch.set_num_threads(1)
-    from oracle import ilqc_oracle as orc
-    env, x0, w = make_batch(1, seed)
-    cfg = dict(ENV_CFG, reg_cont=float(w[0, 0]), reg_lag=float(w[0, 1]), reg_speed=float(w[0, 2]))
-    oenv = orc.make_env(cfg)
-    oenv.init_state = x0[0].clone()
-    t0 = time.time()
-    _, _, m = orc.run_min_algo(oenv, max_iter=iters, algo=ALGO)
-    return len(m["cost"]) - 1, time.time() - t0
+    kind, make_env_, run_ = _cpu_impl()
+    run_(make_env_(dict(env="pendulum", horizon=10, dt=0.02)), max_iter=1, algo=ALGO)
+    return kind
 
 
-def cpu_reference_step(pool, n_proc, step_idx, iters=1):
-    """One bounded sample: n_proc problems of the workload, `iters` solver iteration(s) each, one process per
-    host core (torch.set_num_threads(1)), exactly as BASELINE.md section 4 plans it."""
+def _cpu_worker(args):
+    """`iters` solver iterations of problem `row` of the benchmark's own seeded batch (make_batch(32768, 1236))."""
+    row, iters = args
+    import torch
+    torch.set_num_threads(1)
+    kind, make_env_, run_ = _cpu_impl()
+    _, x0, w = make_batch(32768, 1236)
+    cfg = dict(ENV_CFG, vinit=float(x0[row, 3]), reg_cont=float(w[row, 0]), reg_lag=float(w[row, 1]), reg_speed=float(w[row, 2]))
+    env = make_env_(cfg)
+    env.init_state = x0[row].clone()
     t0 = time.time()
-    res = pool.map(_cpu_worker, [(1236 + 1000 * step_idx + i, iters) for i in range(n_proc)])
+    _, _, m = run_(env, max_iter=iters, algo=ALGO)
     wall = time.time() - t0
-    return sum(r[0] for r in res), wall
+    t = m["time"]          # cumulative min_step time per iteration (run_min_algo.py:78-96)
+    return len(m["cost"]) - 1, wall, t[1] - t[0] if len(t) > 1 else float("nan"), (t[-1] - t[1]) / max(len(t) - 2, 1) if len(t) > 2 else float("nan")
+
+
+def cpu_reference_step(pool, n_proc, step_idx, iters=CPU_ITERS):
+    """One bounded sample: n_proc problems of the workload (rows of the benchmark's batch), `iters` solver iterations
+    each, one process per host core (torch.set_num_threads(1)), as BASELINE.md section 4 / SURVEY 8(d) plan it."""
+    t0 = time.time()
+    res = pool.map(_cpu_worker, [(step_idx * n_proc + i, iters) for i in range(n_proc)])
+    wall = time.time() - t0
+    n_it = sum(r[0] for r in res)
+    t_first = sum(r[2] for r in res) / len(res)
+    t_steady = sum(r[3] for r in res) / len(res)
+    return n_it, wall, t_first, t_steady
+
+
+def cpu_baseline_object(n_it, wall, t_first, t_steady, n_proc, kind, steps):
+    return {"value": n_it / wall, "unit": UNIT, "cores": n_proc, "kind": kind,
+            "sample": f"{n_proc} problems of the same workload (rows of the benchmark batch) x {CPU_ITERS} iterations from cmd=0 per "
+                      f"step, one process per core with 1 torch thread, {steps} step(s), {wall:.1f} s wall; "
+                      + ("the unmodified reference run_min_algo (oracle/_ref)" if kind == "reference" else "oracle/ilqc_oracle.py"),
+            "iteration1_value": n_proc / t_first if t_first == t_first and t_first > 0 else None,
+            "steady_value": n_proc / t_steady if t_steady == t_steady and t_steady > 0 else None,
+            "note": "iteration1 / steady = cores / mean min_step time of iteration 1 (1.1 line-search trips from cmd=0) / of "
+                    "iterations 2.. (4-5 trips, like the steady state of the 20-iteration solve); value = all iterations / wall "
+                    "(includes collect_info)"}
 
 
 def run_reference(args):
@@ -176,29 +221,26 @@ def run_reference(args):
     if rank != 0:
         return
     n_proc = min(os.cpu_count() or 1, args.cpu_procs)
-    # bounded: every step costs ~30-60 s of wall (one reference-style iteration of a H=100 bicycle problem per
-    # core); cap the number of steps so that the run ends within a few minutes and report what was timed
+    # bounded: one step = CPU_ITERS reference iterations of a H=100 bicycle problem per core (~2 min of wall); the number
+    # of steps is capped so that the run ends within a few minutes, and the line reports what was timed
     steps = max(1, min(args.steps, args.ref_max_steps))
-    warm = min(args.warmup, 1)
     ctx = mp.get_context("spawn")
     with ctx.Pool(n_proc) as pool:
-        for i in range(warm):
-            cpu_reference_step(pool, n_proc, 100 + i)
-        its, wall = 0, 0.0
+        kind = pool.map(_cpu_warm, range(n_proc))[0]      # warm-up: imports + a tiny solve per worker
+        its, wall, tf, ts = 0, 0.0, 0.0, 0.0
         for i in range(steps):
-            a, b = cpu_reference_step(pool, n_proc, i)
-            its += a
-            wall += b
+            a, b, c, d = cpu_reference_step(pool, n_proc, i)
+            its += a; wall += b; tf += c / steps; ts += d / steps
     value = its / wall
-    sample = f"{n_proc} problems x 1 iteration per step (one process per core, 1 thread each), {steps} steps"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": 1, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "bicycle car RK4 H=100 dt=0.01 contouring, ddp_linquad_reg (BASELINE configs[3])",
-                   "note": "CPU oracle port of the reference algorithm (torch autograd, float64); reference is pure "
-                           "Python and cannot travel to the GPU box"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_proc, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD,
+                   "note": ("the unmodified reference (pure Python / torch autograd, float64) from oracle/_ref" if kind == "reference"
+                            else "CPU oracle port of the reference algorithm (torch autograd, float64); oracle/_ref absent")
+                           + f"; a step = {n_proc} problems x {CPU_ITERS} iterations (a 32768-problem x 20-iteration step would take days)"},
+        "cpu_baseline": cpu_baseline_object(its, wall, tf, ts, n_proc, kind, steps),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -206,8 +248,134 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------
-def run_ours(args):
+# other BASELINE.json configurations at their per-GPU sizes (device-resident inputs), for the driver's record
+# ------------------------------------------------------------------------------------------------------
+# SURVEY 8(d) frozen table rows: (F_phi, F_cost, F_lin, F_bell, F_roll, nx, nu)
+CONV = {"cfg2": (34, 17, 146, 517, 48, 4, 1), "cfg3": (22, 11, 162, 2274, 70, 6, 3), "cfg4": (356, 150, 6164, 4394, 418, 8, 3),
+        "cfg5": (356, 150, 6164, 4394, 418, 8, 3)}
+
+
+def _profiled(eng, fn):
+    """Run fn() with the per-kernel-class CUDA-event timing on; returns {class: (ms, launches, slots)}."""
     import ctypes as C
+    ms_buf, n_buf, u_buf = (C.c_double * 8)(), (C.c_int64 * 8)(), (C.c_int64 * 8)()
+    import torch
+    eng.lib.ilqc_profile_enable(1)
+    eng.lib.ilqc_profile_read(ms_buf, n_buf, u_buf, 8)
+    out = fn()
+    torch.cuda.synchronize()
+    eng.lib.ilqc_profile_read(ms_buf, n_buf, u_buf, 8)
+    eng.lib.ilqc_profile_enable(0)
+    return out, {c: dict(ms=ms_buf[i], launches=int(n_buf[i]), slots=int(u_buf[i])) for i, c in enumerate(CLASSES)}
+
+
+def _dominant(prof, conv, H, peak_fp64):
+    f_phi, f_cost, f_lin, f_bell, f_roll, nx, nu = conv
+    fl = {"rollout_cost": f_phi + f_cost, "linearize": f_lin, "backward": f_bell, "rollout_candidate": f_roll + f_cost,
+          "adjoint": 2 * (nx * nx + nx * nu)}
+    dom = max(CLASSES, key=lambda c: prof[c]["ms"])
+    pd = prof[dom]
+    ach = fl[dom] * H * pd["slots"] / (pd["ms"] * 1e-3) if pd["ms"] > 0 else 0.0
+    return {"kernel": dom, "ms": round(pd["ms"], 3), "share_of_kernel_time": pd["ms"] / max(sum(p["ms"] for p in prof.values()), 1e-30),
+            "frac_of_fp64_peak": ach / peak_fp64, "convention": "SURVEY 8(d) table row, one lock-step solve with per-launch CUDA events"}
+
+
+def other_configs(eng, peak_fp64, reps=2):
+    """cfg2 (both algorithms), cfg3 (L=8), cfg4 with its nominal ddp_quad_reg, cfg5 (closed-loop MPC): ms per solve,
+    iterations/s (device-resident inputs, CUDA events, `reps` timed solves after one warm-up) and the dominant kernel."""
+    import torch
+    from ilqc_b200.envs import Car, CartPendulum, make_env
+    from ilqc_b200.model_predictive_control import run_mpc_batched
+    dev = eng.device
+    out = {}
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = 0
+        for _ in range(reps):
+            n += fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return n, e0.elapsed_time(e1) * 1e-3
+
+    def solve_case(tag, conv, env, algo, iters, x0, H, **kw):
+        n, secs = timed(lambda: int(eng.solve(env, algo, iters, x0=x0, **kw).n_done.sum()))
+        _, prof = _profiled(eng, lambda: eng.solve(env, algo, iters, x0=x0, scheduler=1, **kw))
+        out[tag] = {"iterations_per_s": n / secs, "ms_per_solve": 1e3 * secs / reps, "batch": int(x0.shape[0]), "iterations": iters,
+                    "algo": algo, "dominant_kernel": _dominant(prof, CONV[conv], H, peak_fp64)}
+
+    g = torch.Generator().manual_seed(1234)
+    env = CartPendulum(horizon=50, dt=0.05, stay_put_time=0.6, x_limits=(-2.0, 2.0))
+    x0 = torch.zeros(16384, 4, dtype=torch.float64)
+    x0[:, 0] = torch.randn(16384, generator=g, dtype=torch.float64)
+    x0 = x0.to(dev)
+    for algo in ("classic_linquad_reg", "ddp_linquad_reg"):
+        solve_case(f"cfg2_cartpole_H50_B16384_{algo}", "cfg2", env, algo, 20, x0, 50)
+    g = torch.Generator().manual_seed(1235)
+    env = Car(model="simple", track="simple", cost="exact", discretization="euler", reg_bar=0.0, horizon=50, dt=0.04)
+    x0 = env.init_state.reshape(1, -1).repeat(65536, 1)
+    x0[:, 3] = 1.0 + 0.01 * torch.randn(65536, generator=g, dtype=torch.float64)
+    x0[:, 5] = x0[:, 3]
+    solve_case("cfg3_simple_car_exact_euler_H50_B65536_L8", "cfg3", env, "ddp_linquad_reg", 20, x0.to(dev), 50, n_candidates=8)
+    env, x0, w = make_batch(32768, 1236)
+    solve_case("cfg4_bicycle_H100_B32768_ddp_quad_reg", "cfg4", env, "ddp_quad_reg", 10, x0.to(dev), 100, weights=w.to(dev))
+    # cfg5: 4096 concurrent MPC episodes per GPU, complex track, window 40 / overlap 39 / 10 iterations, 40 windows
+    g = torch.Generator().manual_seed(1237)
+    env = make_env(dict(env="real_car", track="complex", vref=2.5, reg_cont=1.0, reg_lag=1.0, reg_speed=1.0))
+    xi = torch.randn(4096, 4, generator=g, dtype=torch.float64)
+    x0 = env.init_state.reshape(1, -1).repeat(4096, 1)
+    x0[:, 3] = x0[:, 3] + 0.01 * xi[:, 0]
+    x0[:, 7] = x0[:, 3]
+    w = torch.tensor([1.0, 1.0, 1.0], dtype=torch.float64).reshape(1, 3) + 1e-3 * xi[:, 1:]
+    n_win = 40
+    mpc = lambda: run_mpc_batched(env, full_horizon=40 + n_win - 1, window_size=40, overlap=39, max_iter=10, x0=x0, weights=w,
+                                  engine=eng).n_iterations
+    mpc()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = mpc()
+    e1.record()
+    torch.cuda.synchronize()
+    secs = e0.elapsed_time(e1) * 1e-3
+    _, prof = _profiled(eng, mpc)
+    out["cfg5_mpc_complex_track_4096_episodes_40_windows"] = {
+        "iterations_per_s": n / secs, "windows_per_s": 4096 * n_win / secs, "ms_per_window_solve": 1e3 * secs / n_win, "episodes": 4096,
+        "windows": n_win, "algo": "ddp_linquad_reg", "dominant_kernel": _dominant(prof, CONV["cfg5"], 40, peak_fp64)}
+    return out
+
+
+def parity_object(eng, r_cost, r_cmd, rank0_rows_ok=True):
+    """Reference parity of the benchmarked solve itself (outside the timed region): rows 0..7 of rank 0's batch ARE the 8
+    problems of tests/golden/batch_bcar100.npz (unmodified reference, 20 iterations each).  Free-running chains drift once
+    the iterates are converged, so the per-iteration error, the first iteration beyond 1e-9 and the final
+    cost error are all reported; the strict 1e-9 per-iteration parity is the teacher-forced GPU test over the same rows."""
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "batch_bcar100.npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    rows = g["rows"]
+    n = min(r_cost.shape[1], g["cost"].shape[1])
+    c = r_cost[rows][:, :n].cpu().numpy()
+    err = np.abs(c - g["cost"][:, :n]) / np.abs(g["cost"][:, :n])
+    first = [int(next((k for k in range(n) if not err[p, k] < 1e-9), n)) for p in range(len(rows))]
+    out = {"fixture": "tests/golden/batch_bcar100.npz (unmodified reference, rows 0..7 of this batch)", "rows": [int(x) for x in rows],
+           "iterations_compared": n - 1, "max_rel_err_cost_first_3_iterations": float(err[:, :4].max()),
+           "max_rel_err_cost_per_iteration": [float(x) for x in err.max(0)],
+           "first_iteration_beyond_1e-9_per_row": first, "max_rel_err_final_cost": float(err[:, n - 1].max())}
+    if n == g["cost"].shape[1]:
+        ref_u = g["cmds"][:, -1]
+        u = r_cmd[rows].cpu().numpy()
+        out["max_rel_err_final_cmd"] = float((np.abs(u - ref_u).reshape(len(rows), -1).max(1) / np.abs(ref_u).reshape(len(rows), -1).max(1)).max())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
     import torch
     import torch.distributed as dist
     from ilqc_b200.engine import default_engine
@@ -242,15 +410,13 @@ def run_ours(args):
         return r
 
     lib = eng.lib
-    ms_buf, n_buf, u_buf = (C.c_double * 8)(), (C.c_int64 * 8)(), (C.c_int64 * 8)()
+    lib.ilqc_profile_enable(0)        # no per-launch events inside the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
-        lib.ilqc_profile_enable(1)   # (enabled before the warm-up so that its event pool exists when timing starts)
         for _ in range(args.warmup):
             r = step()
             int(r.n_done.sum().item())   # (same host-side reduction as the timed loop: its kernel loads lazily)
         barrier()
-        lib.ilqc_profile_read(ms_buf, n_buf, u_buf, 8)  # reset
         lib.ilqc_launch_count(1)
         clocks.mark()
         barrier()
@@ -266,9 +432,6 @@ def run_ours(args):
         e1.record()
         barrier()
     n_launches = int(lib.ilqc_launch_count(1))
-    lib.ilqc_profile_read(ms_buf, n_buf, u_buf, 8)
-    lib.ilqc_profile_enable(0)
-    timed = {c: dict(ms=ms_buf[i], launches=int(n_buf[i]), slots=int(u_buf[i])) for i, c in enumerate(CLASSES)}
     per_step_ms = [round(step_ev[i].elapsed_time(step_ev[i + 1]), 2) for i in range(args.steps)]
     print(f"[bench] rank {rank} per-step ms: {per_step_ms}", file=sys.stderr, flush=True)
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -278,6 +441,7 @@ def run_ours(args):
         dist.all_reduce(tot_its, op=dist.ReduceOp.SUM)
     elapsed_s = ms.item() * 1e-3
     value = tot_its.item() / elapsed_s
+    parity = parity_object(eng, r.cost, r.cmd) if rank == 0 else None
 
     # ---- end-to-end through the C ABI with HOST buffers (copies inside the timed region) ----
     # every step copies its inputs (initial states, per-problem cost weights, step sizes) from pinned host memory and
@@ -324,16 +488,13 @@ def run_ours(args):
         return
 
     # ---- roofline of the dominant kernel ----
-    # Per-kernel durations: CUDA events around every launch (on the launching stream) of one extra lock-step
-    # solve of the same batch right after the timed region (`kernels`); the event times collected inside the
-    # timed region itself are reported as `kernels_timed_region`.
-    lib.ilqc_profile_enable(1)
-    lib.ilqc_profile_read(ms_buf, n_buf, u_buf, 8)
-    eng.solve(env, ALGO, iters, x0=x0d, weights=wd, n_candidates=L, scheduler=1)
-    torch.cuda.synchronize()
-    lib.ilqc_profile_read(ms_buf, n_buf, u_buf, 8)
-    lib.ilqc_profile_enable(0)
-    prof = {c: dict(ms=ms_buf[i], launches=int(n_buf[i]), slots=int(u_buf[i])) for i, c in enumerate(CLASSES)}
+    # Per-kernel durations: CUDA events around every launch (on the launching stream) of ONE extra lock-step solve of the
+    # same batch right after the timed region (the timed region itself carries no profiling events).  The same solve
+    # records the line-search trips: needed candidates = trips the sequential reference search would make.
+    rp, prof = _profiled(eng, lambda: eng.solve(env, ALGO, iters, x0=x0d, weights=wd, n_candidates=L, scheduler=1, record_trips=True))
+    iters_done = max(int(rp.n_done.sum().item()), 1)
+    n_c_needed = float(rp.ls_trips.sum().item()) / iters_done
+    n_c_evaluated = prof["rollout_candidate"]["slots"] / iters_done
     dom = max(CLASSES, key=lambda c: prof[c]["ms"])
     kernel_ms_total = sum(p["ms"] for p in prof.values())
     peak_fp64 = eng.fp64_peak(2048)
@@ -343,41 +504,48 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    counters = load_counters()
+    cls = (counters or {}).get("classes", {})
     pd = prof[dom]
     flops = FLOPS_PER_STEP[dom] * 100 * pd["slots"]
     achieved = flops / (pd["ms"] * 1e-3) / 1e12 if pd["ms"] > 0 else 0.0
     bytes_ = BYTES_PER_SLOT[dom] * pd["slots"]
-    exec_flops = EXEC_FLOPS_PER_STEP[dom] * 100 * pd["slots"]
-    exec_tflops = exec_flops / (pd["ms"] * 1e-3) / 1e12 if pd["ms"] > 0 else 0.0
-    traffic = NCU_DRAM_BYTES_PER_SLOT.get(dom)
+    ex_f = cls.get(dom, {}).get("exec_flops_per_slot_step")
+    exec_tflops = ex_f * 100 * pd["slots"] / (pd["ms"] * 1e-3) / 1e12 if (ex_f and pd["ms"] > 0) else None
+    traffic = cls.get(dom, {}).get("dram_bytes_per_slot")
     roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved, "peak": peak_fp64 / 1e12, "unit": "TFLOP/s",
                 "frac": achieved / (peak_fp64 / 1e12),
                 "traffic": None if traffic is None else traffic * pd["slots"] / max(pd["launches"], 1),
-                "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per slot (profiles/r01_ncu_hot_kernels_v3.txt) "
-                                  "x average slots per launch",
+                "traffic_source": None if counters is None else
+                f"ncu dram__bytes_read.sum + dram__bytes_write.sum per slot x average slots per launch; capture: {counters.get('captured')} "
+                f"at commit {counters.get('commit')} (profiles/kernel_counters.json)",
                 "algorithmic_bytes_per_launch_avg": bytes_ / max(pd["launches"], 1),
-                "executed": {"achieved": exec_tflops, "unit": "TFLOP/s", "frac": exec_tflops / (peak_fp64 / 1e12),
-                             "flops_per_slot_step": EXEC_FLOPS_PER_STEP[dom],
-                             "note": "FP64 instructions actually executed (ncu dadd + dmul + 2 dfma per slot-step) / "
-                                     "live CUDA-event time; the convention counts a transcendental as one flop"},
-                "peak_source": "measured DFMA micro-benchmark (ilqc_fp64_peak) on this GPU; nominal 37 TFLOP/s",
+                "executed": None if exec_tflops is None else
+                {"achieved": exec_tflops, "unit": "TFLOP/s", "frac": exec_tflops / (peak_fp64 / 1e12), "flops_per_slot_step": ex_f,
+                 "counters_commit": counters.get("commit"),
+                 "note": "FP64 instructions actually executed (ncu dadd + dmul + 2 dfma per slot-step, profiles/kernel_counters.json) / "
+                         "live CUDA-event time; the convention counts a transcendental as one flop"},
+                "peak_source": "measured DFMA micro-benchmark (ilqc_fp64_peak) on this GPU; nominal 37 TFLOP/s "
+                               "(MEASURED_PEAKS.json holds no FP64 figure)",
                 "flops_per_launch_avg": flops / max(pd["launches"], 1), "ms_per_launch_avg": pd["ms"] / max(pd["launches"], 1),
                 "share_of_kernel_time": pd["ms"] / kernel_ms_total if kernel_ms_total else None,
                 "hbm": {"achieved": bytes_ / (pd["ms"] * 1e-3) / 1e9 if pd["ms"] > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
                         "frac": (bytes_ / (pd["ms"] * 1e-3) / 1e9) / hbm_peak if pd["ms"] > 0 else 0.0,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
                 "convention": "SURVEY.md 8(d) frozen table, cfg4 row",
-                "timing": "CUDA events around every launch of one lock-step solve of the same batch (kernels not overlapped)"}
-    # whole-iteration algorithmic flops: F_iter formula with the measured candidates per iteration
-    n_c = timed["rollout_candidate"]["slots"] / max(timed["linearize"]["slots"] - B * args.steps, 1)
-    f_iter = 100 * (F_LIN + F_PHI + F_COST + n_c * (F_BELL + F_ROLL + F_COST)) + 100 * 2 * (NX * NX + NX * NU)
-    exec_total = sum(EXEC_FLOPS_PER_STEP[c] * 100 * timed[c]["slots"] for c in CLASSES)
+                "timing": "CUDA events around every launch of one lock-step solve of the same batch, after the timed region"}
+    # whole-iteration algorithmic flops: F_iter formula of SURVEY 8(d) with the NEEDED candidates per iteration (the
+    # trips the sequential search makes; speculatively evaluated candidates do not count)
+    f_iter = 100 * (F_LIN + F_PHI + F_COST + n_c_needed * (F_BELL + F_ROLL + F_COST)) + 100 * 2 * (NX * NX + NX * NU)
+    exec_known = all(cls.get(c, {}).get("exec_flops_per_slot_step") for c in CLASSES)
+    exec_total = sum(cls[c]["exec_flops_per_slot_step"] * 100 * prof[c]["slots"] for c in CLASSES) if exec_known else None
+    solve_s = elapsed_s / args.steps
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * elapsed_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "bicycle car RK4 H=100 dt=0.01 contouring, ddp_linquad_reg (BASELINE configs[3], per-GPU slice)",
+        "config": {"workload": WORKLOAD,
                    "batch_per_gpu": B, "global_batch": B * world, "solver_iterations": iters, "line_search_candidates": L, "scheduler": {0: "auto (lock-step)", 1: "lock-step", 2: "asynchronous"}[args.scheduler],
                    "parallelism": f"dp{world} (independent slices, final all-gather only)",
                    "l2": "working set (expansion+gains, >1 GB) is far larger than the 126 MB L2; no flush needed"},
@@ -386,23 +554,30 @@ def run_ours(args):
         "gpu_launches": n_launches,
         "clocks": clocks.summary(),
         "roofline": roofline,
+        "parity": parity,
         "per_step_ms": per_step_ms,
         "kernels": {c: {"ms": round(p["ms"], 3), "launches": p["launches"], "slots": p["slots"]} for c, p in prof.items()},
-        "kernels_timed_region": {c: {"ms": round(p["ms"], 3), "launches": p["launches"], "slots": p["slots"]} for c, p in timed.items()},
-        "solver": {"candidates_per_iteration": n_c, "algorithmic_flops_per_iteration": f_iter,
-                   "algorithmic_tflops": f_iter * value / 1e12, "frac_of_fp64_peak": f_iter * value / peak_fp64,
-                   "executed_tflops_whole_step": exec_total * world / elapsed_s / 1e12,
-                   "executed_frac_of_fp64_peak": exec_total / elapsed_s / peak_fp64},
+        "solver": {"candidates_needed_per_iteration": n_c_needed, "candidates_evaluated_per_iteration": n_c_evaluated,
+                   "algorithmic_flops_per_iteration": f_iter,
+                   "algorithmic_tflops": f_iter * value / world / 1e12, "frac_of_fp64_peak": f_iter * value / world / peak_fp64,
+                   "executed_tflops_whole_step": None if exec_total is None else exec_total / solve_s / 1e12,
+                   "executed_frac_of_fp64_peak": None if exec_total is None else exec_total / solve_s / peak_fp64,
+                   "note": "algorithmic: SURVEY 8(d) F_iter with the needed candidates (per GPU); executed: ncu flop counts x the slots of "
+                           "every launch of the profiled solve / the timed solve time (includes speculative candidates)"},
     }
-    # ---- CPU baseline (rank 0, N=1 only): the oracle port on the host cores, bounded sample ----
+    if world == 1 and not args.no_other_configs:
+        try:
+            line["other_configs"] = other_configs(eng, peak_fp64)
+        except Exception as exc:      # the headline line must survive a failure in the side measurements
+            line["other_configs"] = {"error": repr(exc)}
+    # ---- CPU baseline (rank 0, N=1 only): the reference's CPU implementation on the host cores, bounded sample ----
     if world == 1 and not args.no_cpu_baseline:
         import multiprocessing as mp
         n_proc = min(os.cpu_count() or 1, args.cpu_procs)
         with mp.get_context("spawn").Pool(n_proc) as pool:
-            c_its, c_wall = cpu_reference_step(pool, n_proc, 0)
-        line["cpu_baseline"] = {"value": c_its / c_wall, "unit": UNIT, "cores": n_proc, "kind": "port",
-                                "sample": f"{n_proc} problems of the same workload x 1 iteration, one process per core "
-                                          f"(oracle/ilqc_oracle.py), {c_wall:.1f} s wall"}
+            kind = pool.map(_cpu_warm, range(n_proc))[0]
+            c_its, c_wall, tf, ts = cpu_reference_step(pool, n_proc, 0)
+        line["cpu_baseline"] = cpu_baseline_object(c_its, c_wall, tf, ts, n_proc, kind, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -419,8 +594,9 @@ def main():
     ap.add_argument("--candidates", type=int, default=128, help="max line-search candidates per problem per round")
     ap.add_argument("--scheduler", type=int, default=0, help="0 auto, 1 lock-step iterations, 2 asynchronous")
     ap.add_argument("--cpu-procs", type=int, default=64)
-    ap.add_argument("--ref-max-steps", type=int, default=3)
+    ap.add_argument("--ref-max-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -10,7 +10,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 CUDA_LIB_PATH = os.path.join(PKG, "libilqc_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 # enums of include/ilqc_b200.h
 MODEL_PENDULUM, MODEL_CARTPOLE, MODEL_CAR_SIMPLE, MODEL_CAR_BICYCLE = 0, 1, 2, 3
 INT_EULER, INT_RK4_CST, INT_RK4 = 0, 1, 2
@@ -78,6 +78,10 @@ PROTOTYPES = {
     "ilqc_mpc_num_windows": (C.c_int, [C.c_int] * 3),
     "ilqc_mpc_workspace_bytes": (C.c_size_t, [_MP, _AP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "ilqc_mpc": (C.c_int, [_MP, _AP, C.c_int, _p] + [C.c_int] * 7 + [_p, C.POINTER(_i), _p, _p, _p, _p, C.c_size_t, _p]),
+    "ilqc_newton_dense_workspace_bytes": (C.c_size_t, [_MP, C.c_int]),
+    "ilqc_newton_dense": (C.c_int, [_MP, C.c_int] + [_p] * 8 + [C.c_size_t, _p]),
+    "ilqc_traj_jacobian_workspace_bytes": (C.c_size_t, [_MP, C.c_int]),
+    "ilqc_traj_jacobian": (C.c_int, [_MP, C.c_int, _p, _p, _p, _p, C.c_size_t, _p]),
     "ilqc_to_soa": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
     "ilqc_from_soa": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
     "ilqc_profile_enable": (C.c_int, [C.c_int]),

@@ -72,9 +72,14 @@ def run_min_algo(env, max_iter: int = 10, algo: str = "ddp_linquad_reg", stepsiz
     Restart semantics of the reference are kept: with `past_metrics` the solve continues from iteration
     past_metrics['iteration'][-1] up to `max_iter` and appends to the same lists."""
     if compute_min_sev:
+        # (the reference itself raises here: `format_types.append["scientific"]`, run_min_algo.py:184;
+        #  compute_min_sing_eigval_jac below is the function it would have called)
         raise NotImplementedError("compute_min_sev raises in the reference too (run_min_algo.py:184)")
     import time
     _, _, step_mode = check_nomenclature(algo)
+    if "newton" in algo:
+        return _run_min_algo_newton(env, max_iter, algo, stepsize, line_search, handle_bad_dir, prev_cmd, optim_aux_vars,
+                                    past_metrics)
     if optim_aux_vars is not None:
         stepsize = float(optim_aux_vars["stepsize"])
     elif stepsize is None:
@@ -115,3 +120,63 @@ def run_min_algo(env, max_iter: int = 10, algo: str = "ddp_linquad_reg", stepsiz
         for k in rows:
             print("{:<12d}{:<16.6e}{:<16.2e}{:<16.2e}".format(it0 + k, cost[k], gn[k], srep[k]))
     return cmd_opt, dict(stepsize=float(r.stepsize[0])), metrics
+
+
+def _run_min_algo_newton(env, max_iter, algo, stepsize, line_search, handle_bad_dir, prev_cmd, optim_aux_vars, past_metrics):
+    """`newton_*` (run_min_algo.py:50-100 with min_step's newton_oracle branch, algos_steps.py:311-315): the dense Newton
+    step on the flattened problem, a diagnostic of the reference for ONE problem.  The loop is the reference's; every
+    number comes from the device (`ilqc_newton_dense` for the direction, `ilqc_rollout_cost` for the line search's
+    objective, `ilqc_grad_obj` for the metrics)."""
+    import time
+    from .algos_steps import min_step
+    cmd = (torch.as_tensor(prev_cmd, dtype=torch.float64).detach().clone() if prev_cmd is not None
+           else torch.zeros(env.horizon, env.dim_ctrl, dtype=torch.float64))
+    _, approx, step_mode = check_nomenclature(algo)
+    if optim_aux_vars is not None:
+        stepsize = optim_aux_vars["stepsize"]
+    elif stepsize is None:
+        stepsize = 100.0 if "reg" in step_mode else 1.0
+    eng = env._engine()
+
+    def info(cmd, costs, iteration, stepsize, t_iter, metrics):
+        cost = float(sum(costs)) if costs is not None else float("nan")
+        ex = eng.linearize(env, env.init_state.reshape(1, -1), cmd.reshape(1, *cmd.shape), t0=env.init_time_iter)
+        gn = float(eng.grad_obj(ex)[1][0])
+        row = dict(iteration=iteration, time=(0.0 if iteration == 0 else metrics["time"][-1]) + t_iter, cost=cost,
+                   norm_grad_obj=gn, stepsize=stepsize, algo=algo)
+        if metrics is None:
+            return {k: [v] for k, v in row.items()}
+        for k, v in row.items():
+            metrics[k].append(v)
+        return metrics
+
+    traj, costs = env.forward(cmd, approx=approx)
+    if past_metrics is None:
+        metrics, iteration = info(cmd, costs, 0, stepsize, 0.0, None), 0
+    else:
+        metrics, iteration = past_metrics, past_metrics["iteration"][-1]
+    status = check_cvg_status(metrics, verbose=False)
+    while status == "running" and iteration < max_iter:
+        tic = time.time()
+        cmd_new, traj, costs, stepsize = min_step(env, traj, costs, cmd, stepsize, line_search, algo, handle_bad_dir)
+        iteration += 1
+        if cmd_new is None:   # collect_info differentiates a None command in the reference: the run ends here
+            metrics = info(cmd, None, iteration, stepsize, time.time() - tic, metrics)
+            cmd = None
+            break
+        cmd = cmd_new
+        metrics = info(cmd, costs, iteration, stepsize, time.time() - tic, metrics)
+        status = check_cvg_status(metrics, verbose=False)
+    return (cmd.detach() if cmd is not None else None), dict(stepsize=stepsize), metrics
+
+
+def compute_min_sing_eigval_jac(cmd: torch.Tensor, env) -> float:
+    """run_min_algo.py:103-124: smallest singular value of G = J J^T, J = d traj[1:] / d cmd (H nx x H nu).  J comes
+    from the sensitivity kernel (`ilqc_traj_jacobian`); the Gram product and the singular values are library calls on the
+    device.  (G has rank <= H nu < H nx, so the reference's number is rounding noise around zero for every env of the
+    toolbox; the Jacobian itself is what the parity test compares.)"""
+    eng = env._engine()
+    cmd = torch.as_tensor(cmd, dtype=torch.float64).detach()
+    jac = eng.traj_jacobian(env, env.init_state.reshape(1, -1), cmd.reshape(1, *cmd.shape), t0=env.init_time_iter)[0]
+    s = torch.linalg.svdvals(jac @ jac.t())
+    return float(s.min())

@@ -5,6 +5,7 @@
 #include "solver.inl"
 #include "solver_async.inl"
 #include "mpc.inl"
+#include "newton_dense.inl"
 
 namespace ilqc {
 int dense_lq_backward(int nx, int nu, int H, int B, int L, const double* A, const double* Bm, const double* p,
@@ -409,6 +410,81 @@ int ilqc_mpc(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const dou
   ILQC_CHECK(dev_sync(st));
 #undef ILQC_CHECK
   if (cmd_len_host) *cmd_len_host = curr;
+  return ILQC_LAUNCH_OK();
+}
+
+// ---- dense Newton step / trajectory Jacobian (diagnostics of the reference) --------------------------------
+size_t ilqc_newton_dense_workspace_bytes(const ilqc_model_desc* m, int B) {
+  Dims d;
+  if (get_dims(m, &d) || B <= 0 || d.nx > kNdMaxNx || d.nu > kNdMaxNu) return 0;
+  NdCarve c;
+  nd_carve(&c, d.nx, d.nu, m->horizon, B, true);
+  return c.total;
+}
+int ilqc_newton_dense(const ilqc_model_desc* m, int B, const double* x0, const double* cmd, const double* reg, double* dir,
+                      double* opt, double* grad, double* hess, void* workspace, size_t workspace_bytes, void* stream) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (B <= 0 || !x0 || !cmd || !reg || !dir || !opt) return ILQC_E_ARG;
+  if (d.nx > kNdMaxNx || d.nu > kNdMaxNu) return ILQC_E_UNSUPPORTED;
+  const int H = m->horizon, n = H * d.nu;
+  if ((long long)B * n > 0x7fffffffLL) return ILQC_E_ARG;
+  NdCarve c;
+  nd_carve(&c, d.nx, d.nu, H, B, true);
+  if (!workspace || workspace_bytes < c.total) return ILQC_E_WORKSPACE;
+  stream_t st = (stream_t)stream;
+  char* base = (char*)workspace;
+  auto at = [&](size_t off) { return (double*)(base + off); };
+  double* g = at(c.grad);
+  double* hs = at(c.hess);
+#define ILQC_CHECK(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+  // first-order pass: A, B, p, P, q, Q ; costate and gradient ; second pass: dynamics Hessians contracted with it
+  ILQC_FOR_MODEL(effective_model(*m), ILQC_CHECK(LM::expand_dense(*m, B, x0, cmd, 1, at(c.A), at(c.Bm), at(c.p), at(c.P), at(c.q), at(c.Q),
+                                                           nullptr, nullptr, nullptr, nullptr, st)));
+  NdDense E{d.nx, d.nu, H, B, at(c.A), at(c.Bm), at(c.p), at(c.P), at(c.q), at(c.Q), at(c.Hxx), at(c.Hxu), at(c.Huu)};
+  ILQC_LAUNCH((nd_costate_kernel), B, 64, st, E, at(c.lam), g);
+  ILQC_FOR_MODEL(effective_model(*m), ILQC_CHECK(LM::expand_dense(*m, B, x0, cmd, 2, at(c.A), at(c.Bm), at(c.p), at(c.P), at(c.q), at(c.Q),
+                                                           at(c.lam), at(c.Hxx), at(c.Hxu), at(c.Huu), st)));
+  ILQC_LAUNCH((nd_tangent_kernel), B * n, 128, st, E, at(c.D), (double*)nullptr);
+  ILQC_LAUNCH((nd_hess_kernel), B * n, 128, st, E, at(c.D), hs);
+#if defined(ILQC_HOSTSIM)
+  ILQC_LAUNCH((nd_solve_kernel), B, 1, st, B, n, d.nu, hs, g, reg, at(c.M), at(c.rhs), dir, opt);
+#else
+  nd_solve_kernel<<<B, kNdSolveThreads, 0, st>>>(B, n, d.nu, hs, g, reg, at(c.M), at(c.rhs), dir, opt);
+  ++launch_counter();
+#endif
+  if (grad) ILQC_CHECK(dev_d2d(grad, g, sizeof(double) * (size_t)n * B, st));
+  if (hess) ILQC_CHECK(dev_d2d(hess, hs, sizeof(double) * (size_t)n * n * B, st));
+#undef ILQC_CHECK
+  return ILQC_LAUNCH_OK();
+}
+size_t ilqc_traj_jacobian_workspace_bytes(const ilqc_model_desc* m, int B) {
+  Dims d;
+  if (get_dims(m, &d) || B <= 0 || d.nx > kNdMaxNx || d.nu > kNdMaxNu) return 0;
+  NdCarve c;
+  nd_carve(&c, d.nx, d.nu, m->horizon, B, false);
+  return c.total;
+}
+int ilqc_traj_jacobian(const ilqc_model_desc* m, int B, const double* x0, const double* cmd, double* jac, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  Dims d;
+  int rc = get_dims(m, &d);
+  if (rc) return rc;
+  if (B <= 0 || !x0 || !cmd || !jac) return ILQC_E_ARG;
+  if (d.nx > kNdMaxNx || d.nu > kNdMaxNu) return ILQC_E_UNSUPPORTED;
+  const int H = m->horizon, n = H * d.nu;
+  if ((long long)B * n > 0x7fffffffLL) return ILQC_E_ARG;
+  NdCarve c;
+  nd_carve(&c, d.nx, d.nu, H, B, false);
+  if (!workspace || workspace_bytes < c.total) return ILQC_E_WORKSPACE;
+  stream_t st = (stream_t)stream;
+  char* base = (char*)workspace;
+  auto at = [&](size_t off) { return (double*)(base + off); };
+  ILQC_FOR_MODEL(effective_model(*m), { int rc2 = LM::expand_dense(*m, B, x0, cmd, 1, at(c.A), at(c.Bm), at(c.p), at(c.P), at(c.q), at(c.Q),
+                                                                nullptr, nullptr, nullptr, nullptr, st); if (rc2) return rc2; });
+  NdDense E{d.nx, d.nu, H, B, at(c.A), at(c.Bm), at(c.p), at(c.P), at(c.q), at(c.Q), nullptr, nullptr, nullptr};
+  ILQC_LAUNCH((nd_tangent_kernel), B * n, 128, st, E, (double*)nullptr, jac);
   return ILQC_LAUNCH_OK();
 }
 

@@ -391,6 +391,46 @@ class Engine:
         return (self.from_soa(cmd[:T * nu], B, T, nu), cost.permute(2, 0, 1).contiguous(), status.t().contiguous(),
                 n_done.t().contiguous())
 
+    # ---- dense diagnostics of the reference ------------------------------------------------------------------
+    def newton_dense(self, env, x0, cmd, reg, t0=None, weights=None, want_hess=False):
+        """newton_oracle's linear algebra (algos_steps.py:46-102) for a batch: dir [B,H,nu] = -(Hess + reg I)^-1 grad,
+        opt [B] = dir.grad/2 (+ grad [B,H,nu] and, with want_hess, the dense Hessian [B,H nu,H nu])."""
+        cmd = self._dev(cmd)
+        B, H, nu = cmd.shape
+        x0 = self._x0(env, x0, B)
+        d, keep = self.make_desc(env, H, B, t0, weights)
+        nbytes = self.lib.ilqc_newton_dense_workspace_bytes(C.byref(d), B)
+        if nbytes == 0:
+            raise _lib.IlqcError("ilqc_newton_dense_workspace_bytes: unsupported dimensions")
+        ws = self.workspace(nbytes)
+        x0s, cmds = self.to_soa(x0), self.to_soa(cmd)
+        regs = self._dev(reg).reshape(B)
+        n = H * nu
+        dirs, opt, grad = self.empty(n, B), self.empty(B), self.empty(n, B)
+        hess = self.empty(B, n, n) if want_hess else None
+        _lib.check(self.lib.ilqc_newton_dense(C.byref(d), B, self._ptr(x0s), self._ptr(cmds), self._ptr(regs), self._ptr(dirs),
+                                              self._ptr(opt), self._ptr(grad), self._ptr(hess), self._ptr(ws), C.c_size_t(nbytes),
+                                              self._stream()), "ilqc_newton_dense")
+        out = (self.from_soa(dirs, B, H, nu), opt, self.from_soa(grad, B, H, nu))
+        return out + (hess,) if want_hess else out[:2]
+
+    def traj_jacobian(self, env, x0, cmd, t0=None, weights=None):
+        """d traj[1:] / d cmd for a batch: [B, H nx, H nu] (compute_min_sing_eigval_jac, run_min_algo.py:103-124)."""
+        cmd = self._dev(cmd)
+        B, H, nu = cmd.shape
+        x0 = self._x0(env, x0, B)
+        d, keep = self.make_desc(env, H, B, t0, weights)
+        nx, _ = self.dims(d)
+        nbytes = self.lib.ilqc_traj_jacobian_workspace_bytes(C.byref(d), B)
+        if nbytes == 0:
+            raise _lib.IlqcError("ilqc_traj_jacobian_workspace_bytes: unsupported dimensions")
+        ws = self.workspace(nbytes)
+        x0s, cmds = self.to_soa(x0), self.to_soa(cmd)
+        jac = self.empty(B, H * nx, H * nu)
+        _lib.check(self.lib.ilqc_traj_jacobian(C.byref(d), B, self._ptr(x0s), self._ptr(cmds), self._ptr(jac), self._ptr(ws),
+                                               C.c_size_t(nbytes), self._stream()), "ilqc_traj_jacobian")
+        return jac
+
     def fastmath_eval(self, fn, a, b=None):
         """Self-test of csrc/fastmath.cuh: fn in {sincos, atan2, atan, div, rcp, sqrt_rsqrt}, elementwise."""
         code = ["sincos", "atan2", "atan", "div", "rcp", "sqrt_rsqrt"].index(fn)

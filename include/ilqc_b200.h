@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ILQC_ABI_VERSION 2
+#define ILQC_ABI_VERSION 3
 
 enum { ILQC_E_ARG = -1, ILQC_E_UNSUPPORTED = -2, ILQC_E_WORKSPACE = -3 };
 
@@ -214,6 +214,24 @@ int ilqc_mpc(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const dou
              int window_size, int overlap, int max_iter, int optim_on_full_window, int keep_applying_last_ctrl,
              int max_windows, double* cmd, int32_t* cmd_len_host, double* cost, int32_t* status, int32_t* n_done,
              void* workspace, size_t workspace_bytes, void* stream);
+
+/* newton_oracle (algorithms/algos_steps.py:46-102; the dense cross-check of tests/test_newton.py): Newton step on the
+ * flattened problem.  The (H nu x H nu) Hessian of the total cost is assembled from the analytic second-order expansion
+ * (costate + one second-order adjoint sweep per column) instead of autodiff, then (Hessian + reg I) d = -grad is solved
+ * by LU with partial pivoting in one thread block per problem (torch.linalg.solve).  A diagnostic: nx <= 8, nu <= 9,
+ * memory grows like B (H nu)^2.
+ * x0 [nx][B], cmd [H][nu][B], reg [B] ; out dir [H][nu][B], opt [B] = dir . grad / 2 ; optional grad [H][nu][B],
+ * hess [B][H nu][H nu] (row-major per problem). */
+size_t ilqc_newton_dense_workspace_bytes(const ilqc_model_desc* m, int B);
+int ilqc_newton_dense(const ilqc_model_desc* m, int B, const double* x0, const double* cmd, const double* reg,
+                      double* dir, double* opt, double* grad, double* hess, void* workspace, size_t workspace_bytes,
+                      void* stream);
+/* Jacobian of the trajectory traj[1:] with respect to the controls, the matrix compute_min_sing_eigval_jac
+ * (algorithms/run_min_algo.py:103-124) builds with auto_multi_grad: jac [B][H nx][H nu], row (t-1) nx + i = state i of
+ * x_t, column s nu + k = control k of step s (zero for s >= t). */
+size_t ilqc_traj_jacobian_workspace_bytes(const ilqc_model_desc* m, int B);
+int ilqc_traj_jacobian(const ilqc_model_desc* m, int B, const double* x0, const double* cmd, double* jac,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* [B][R][C] (reference layout, batch outermost) <-> [R][C][B] (engine layout) on the device. */
 int ilqc_to_soa(const double* src, double* dst, int B, int n, void* stream);

@@ -279,3 +279,46 @@ def test_riccati_vs_dense_newton_batch(cuda_engine):
 
 def test_time_parallel_expansion(cuda_engine):
     pc.check_time_parallel_expansion(cuda_engine)
+
+
+# ---- batched reference traces at SURVEY 8(d)'s sampling plan (tests/golden/make_golden_batch.py) -------------------
+BATCHES = pc.golden_names("batch_")
+
+
+@pytest.mark.parametrize("name", BATCHES)
+def test_batch_teacher_forced(cuda_engine, name):
+    """EVERY stored iterate of every problem of the fixture as one batch of one-iteration solves: the 8 seeded headline
+    problems (bicycle H=100 ddp_linquad_reg, rows 0..7 of bench.py's batch) x 20 iterations, 3 x 2 of ddp_quad_reg at H=100,
+    64 x 8 / 16 x 2 at H=25, 64 x 20 cart-pendulum (both algorithms) and simple car: new cost, new controls, step-size
+    state, gradient norms, reported step within 1e-9 relative (a measured, reference-derived tolerance on the few rows
+    where the reference itself amplifies last-bit noise beyond that, tests/golden/make_sensitivity.py) and identical
+    line-search trip counts."""
+    worst = pc.check_batch_teacher_forced(cuda_engine, name)
+    print(name, worst)
+
+
+@pytest.mark.parametrize("name", BATCHES)
+def test_batch_free_running(cuda_engine, name):
+    """Free-running solves of the same problems: every problem follows the reference for at least its first 3 iterations
+    at 1e-9; the first diverging iteration (SURVEY section 4 statistic) is printed."""
+    first = pc.check_batch_free(cuda_engine, name)
+    print(name, "first diverging iteration per problem:", first.tolist())
+
+
+def test_headline_rows_inside_full_batch(cuda_engine):
+    """The 8 reference problems are rows 0..7 of the benchmark's own seeded batch (bench.py make_batch(32768, 1236)):
+    solved INSIDE the full 32768-problem batch, 20 iterations, they are bit-identical to the same rows solved alone and
+    follow the reference trace (per-iteration cost 1e-9 while the chain has not drifted; final cost 1e-6)."""
+    from bench import make_batch
+    g = pc.golden("batch_bcar100")
+    env, x0, w = make_batch(32768, 1236)
+    rows = torch.as_tensor(g["rows"])
+    assert pc.relerr(x0[rows], g["x0"]) < 1e-15 and pc.relerr(w[rows], g["weights"]) < 1e-15
+    r = cuda_engine.solve(env, "ddp_linquad_reg", 20, x0=x0, weights=w)
+    ra = cuda_engine.solve(env, "ddp_linquad_reg", 20, x0=x0[rows], weights=w[rows])
+    dev = rows.to(r.cost.device)
+    assert torch.equal(r.cost[dev], ra.cost) and torch.equal(r.cmd[dev], ra.cmd)
+    err = np.abs(r.cost[dev].cpu().numpy() - g["cost"]) / np.abs(g["cost"])
+    first = [next((k for k in range(21) if not err[p, k] < 1e-9), 21) for p in range(len(rows))]
+    print("headline rows: first diverging iteration", first, "final cost rel err", err[:, -1])
+    assert min(first) > 3 and err[:, -1].max() < 1e-6

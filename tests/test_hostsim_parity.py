@@ -53,3 +53,21 @@ def test_riccati_vs_dense_newton_batch(sim_engine):
 
 def test_time_parallel_expansion(sim_engine):
     pc.check_time_parallel_expansion(sim_engine)
+
+
+# ---- batched reference traces at SURVEY 8(d)'s sampling plan (tests/golden/make_golden_batch.py) -------------------
+BATCHES = pc.golden_names("batch_")
+
+
+@pytest.mark.parametrize("name", BATCHES)
+def test_batch_teacher_forced(sim_engine, name):
+    """Every stored iterate of every problem of the fixture (8 headline problems x 20 iterations, 64 x 8 at H=25, 64 x 20
+    cart-pendulum / simple car, the ddp_quad_reg rows): cost, controls, step-size state, gradient norm, reported step
+    within 1e-9 relative and identical line-search trip counts."""
+    pc.check_batch_teacher_forced(sim_engine, name)
+
+
+@pytest.mark.parametrize("name", BATCHES)
+def test_batch_free_running(sim_engine, name):
+    first = pc.check_batch_free(sim_engine, name)
+    assert first.min() > 3
