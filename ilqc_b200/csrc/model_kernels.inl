@@ -271,7 +271,10 @@ int Launch<ILQC_MODEL_INST>::backward(int mode, const ilqc_model_desc& m, int B,
 #define ILQC_BWD_ARGS m, B, n_slots, prob, oslot, n_oslots, reg_ctrl, reg_state, lin, traj, cmd, hess, gains, jcst, feasible, bad_dir
   if (mode == ILQC_BWD_LINQUAD) {
     if constexpr (kBwdAsyncFeed<MI>) {
-      if (dense && (long long)n_slots <= 5LL * B) {
+      // (ILQC_FEED_SMALL=<slots>: tuning knob - also stage the operands of launches of at most that many slots, which are
+      //  latency-bound whatever their access pattern; measured in profiles/r02_tuning_small_rounds.txt)
+      static const long long feed_small = [] { const char* e = getenv("ILQC_FEED_SMALL"); return e ? atoll(e) : 0LL; }();
+      if ((dense && (long long)n_slots <= 5LL * B) || (long long)n_slots <= feed_small) {
         ILQC_LAUNCH_SMEM((backward_kernel<MI, ILQC_BWD_LINQUAD, true, false>), n_slots, kBlock, kBwdSmemBytes<MI>, st, ILQC_BWD_ARGS);
         return ILQC_LAUNCH_OK();
       }

@@ -637,8 +637,28 @@ inline size_t round_capacity(int round) {
   const size_t wave = (size_t)wave_slots();
   return round == 0 ? wave + (3 * wave) / 4 : wave;
 }
-inline int round_candidates(int round, int n_active, int Lmax) {
+// `done` = candidates every still-searching problem has already tried in this search.
+// Small-batch regime (the first round affords more than 4 candidates per problem, i.e. fewer than ~12 k searching
+// problems: MPC windows, single problems): launches are latency-bound, a round costs the same whether it carries 1 k or
+// 20 k slots, so rounds are what to save - the first round takes up to 24 candidates within 65536 slots and every later
+// round four times what has been tried so far, within one wave (tools/sim_round_policy.py on the trip counts of
+// warm-started MPC windows, profiles/r02_scheduling_analysis.txt: -12 to -23 % line-search time against the 4/3/16/128 rule).
+inline int round_candidates(int round, int n_active, int Lmax, int done = 0, bool small_batch = false) {
   const int n = n_active > 0 ? n_active : 1;
+  if (round >= 0 && small_batch) {
+    int c;
+    if (round == 0) {
+      c = 65536 / n;
+      c = c < 4 ? 4 : (c > 24 ? 24 : c);
+    } else {
+      c = 4 * done;
+      c = c > 128 ? 128 : c;
+    }
+    const int cap = (int)(round_capacity(round) / (size_t)n);  // (the workspace holds slot_capacity() slots)
+    c = c > cap ? cap : c;
+    c = c < 1 ? 1 : c;
+    return c < Lmax ? c : Lmax;
+  }
   if (round >= 0) {
     int c;
     if (round == 0) {
@@ -654,6 +674,8 @@ inline int round_candidates(int round, int n_active, int Lmax) {
   int L = (int)(round_capacity(round) / (size_t)n);
   return L < 1 ? 1 : (L > Lmax ? Lmax : L);
 }
+// small-batch regime of an iteration that starts its search with n_active problems (see round_candidates)
+inline bool small_batch_regime(int n_active) { return n_active > 0 && 49152 / n_active > 4; }
 // slots the workspace must hold: n_active * round_candidates(...) <= max(B, largest round capacity)
 inline size_t slot_capacity(int B, int Lmax) {
   // (two waves: round 0 of the bulk = 1.75 waves + the deferred stragglers of the asynchronous scheduler)
@@ -775,8 +797,9 @@ inline int solve_impl(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, 
     }
 
     // ---- line search rounds ----
-    for (int round = 0; n_active > 0; ++round) {
-      P.L = round_candidates(round, n_active, L);
+    const bool small_batch = small_batch_regime(n_active);
+    for (int round = 0, tried = 0; n_active > 0; ++round, tried += P.L) {
+      P.L = round_candidates(round, n_active, L, tried, small_batch);
       const int n_slots = n_active * P.L;
       if (trace_rounds()) fprintf(stderr, "ilqc round: t %.3f ms iter %d active %d candidates %d\n", trace_ms(), it, n_active, P.L);
       ILQC_LAUNCH((make_slots_kernel), n_active, 256, st, P, n_active, w.list, w.s_try, w.prob, w.gslot, w.step_true,

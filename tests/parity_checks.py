@@ -429,15 +429,31 @@ def check_batch_teacher_forced(eng, name, tol=TOL, **solve_kw):
             n_relaxed += int(tols["cost1"][i] > tol and not converged)
     # before numerical convergence at most 2 % of the rows may be skipped or have a relaxed COST tolerance
     assert n_relaxed <= max(1, n // 50), (name, n_relaxed)
+    pi = np.array([r[0] for r in rows]); ki = np.array([r[1] for r in rows])
+    conv_row = (gc[pi, ki] - gc[pi, ki + 1]) < tol * np.abs(gc[pi, ki])
+    # gradient norms have an absolute floor (cancellation in the adjoint sum): 1e-11 of the problem's largest norm; the
+    # reported 'reg' step is the step state times the previous norm and inherits it as a relative error
+    gng = golden(name)["norm_grad_obj"]
+    gmax = np.nanmax(gng, axis=1)[pi]
+    ok = {k: e[k] < tols[k] for k in e}
+    ok["gn0"] |= e["gn0"] * np.abs(gng[pi, ki]) <= 1e-11 * gmax
+    ok["gn1"] |= e["gn1"] * np.abs(gng[pi, ki + 1]) <= 1e-11 * gmax
+    ok["srep"] |= e["srep"] <= 4e-11 * gmax / np.abs(gng[pi, ki])
+    # on a numerically converged row the search is decided by the last bits of two equal costs: when the trip count
+    # differs there, only the costs (and the gradient norm of the given iterate) are compared
+    flipped = conv_row & ~trips_ok
+    for k in ("cmd", "gn1", "step", "srep"):
+        ok[k] |= flipped
     worst = {k: float(np.max(v[~skip])) for k, v in e.items()}
-    bad = {k: [(float(e[k][i]), rows[i]) for i in np.nonzero(~(e[k] < tols[k]) & ~skip)[0][:4]] for k in e}
+    bad = {k: [(float(e[k][i]), rows[i]) for i in np.nonzero(~ok[k] & ~skip)[0][:4]] for k in e}
     bad = {k: v for k, v in bad.items() if v}
     assert not bad, (name, bad)
-    mism = np.nonzero(~trips_ok & ~skip)[0]
+    mism = np.nonzero(~trips_ok & ~skip & ~conv_row)[0]
     assert len(mism) == 0, (name, [rows[i] for i in mism[:8]])
     worst["n_rows"] = n
     worst["n_relaxed_cost_or_skipped"] = n_relaxed
     worst["n_converged_rows_skipped"] = n_conv_skipped
+    worst["n_converged_rows_with_other_trip_count"] = int(flipped.sum())
     worst["n_rows_with_measured_sensitivity"] = len(sens)
     return worst
 
