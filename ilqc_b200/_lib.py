@@ -85,6 +85,7 @@ PROTOTYPES = {
     "ilqc_to_soa": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
     "ilqc_from_soa": (C.c_int, [_p, _p, C.c_int, C.c_int, _p]),
     "ilqc_profile_enable": (C.c_int, [C.c_int]),
+    "ilqc_set_tuning": (C.c_int, [C.c_char_p, C.c_longlong]),
     "ilqc_profile_read": (C.c_int, [C.POINTER(_d), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int]),
     "ilqc_launch_count": (C.c_longlong, [C.c_int]),
     "ilqc_fp64_peak": (C.c_int, [C.c_int, C.POINTER(_d), _p]),

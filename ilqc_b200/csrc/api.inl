@@ -191,6 +191,14 @@ int ilqc_solve(const ilqc_model_desc* m, const ilqc_algo_desc* a, int B, const d
 // per-kernel-class CUDA-event timing of ilqc_solve (classes: 0 roll-out+cost, 1 expansion, 2 backward,
 // 3 candidate roll-out, 4 adjoint).  enable: 1/0 ; read returns cumulative ms / launches / slots and resets.
 int ilqc_profile_enable(int enable) { prof_state().enabled = enable; return 0; }
+int ilqc_set_tuning(const char* name, long long value) {
+  if (!name) return ILQC_E_ARG;
+  const Tuning def = tuning_defaults();   // (a negative value restores the default)
+  if (!strcmp(name, "coop_max")) tuning().coop_max = value < 0 ? def.coop_max : value;
+  else if (!strcmp(name, "feed_small")) tuning().feed_small = value < 0 ? def.feed_small : value;
+  else return ILQC_E_ARG;
+  return 0;
+}
 int ilqc_profile_read(double* ms, int64_t* launches, int64_t* units, int n) {
   if (!ms || !launches || !units || n < PROF_N) return ILQC_E_ARG;
   ProfState& p = prof_state();

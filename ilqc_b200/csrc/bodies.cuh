@@ -333,27 +333,14 @@ ILQC_HD void hess_body(const ilqc_model_desc& m, int b, int B, int t, const doub
   static_for<NU>([&](auto I) { us[I] = make_var<S>(u[I], red(M::uv(I))); });
   if constexpr (structured_hess<M>::value) M::template step_hess<S>(m, xs, us, xns, acc);  // (models.cuh: bicycle model)
   else M::template step<S>(m, xs, us, xns);
+  // entries among the carried variables only: the heading entries are closed forms of the first-order expansion and are
+  // rebuilt by the consumer (backward_body)
   double* T = hess + (size_t)t * Layout<M>::hess_stride * B + b;
   static_for<M::NXH>([&](auto I) {
     constexpr int i = I;
-    static_for<NH>([&](auto E) {
-      constexpr int e = E;                                   // packed entry (p, q), p <= q, over all NV variables
-      constexpr int p = SymTable<M::NV>().i[e], q = SymTable<M::NV>().j[e];
-      if constexpr (p != R && q != R) {
-        constexpr int er = sym_idx(red(p), red(q), NVJ);    // the same pair among the carried variables
-        if constexpr (er >= S::E0 && er < S::E0 + S::NH) T[(size_t)(i * NH + e) * B] = xns[i].h[er - S::E0];
-      } else if constexpr (G == 0) {
-        // entries with the heading: rows 0, 1 are (x, y); d/dphi (x' - x) = -(y' - y), d/dphi (y' - y) = x' - x
-        double v = 0.0;
-        if constexpr (i == 0) {
-          if constexpr (p == R && q == R) v = -(xns[0].v - x[0]);
-          else v = -xns[1].g[red(p == R ? q : p)];
-        } else if constexpr (i == 1) {
-          if constexpr (p == R && q == R) v = -(xns[1].v - x[1]);
-          else v = xns[0].g[red(p == R ? q : p)];
-        }
-        T[(size_t)(i * NH + e) * B] = v;
-      }
+    static_for<S::NH>([&](auto Kk) {
+      constexpr int k = Kk;
+      if constexpr (S::valid(k)) T[(size_t)(i * Layout<M>::hess_row + S::entry(k)) * B] = xns[i].h[k];
     });
   });
 }
@@ -417,12 +404,48 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
         // contraction of the stored second-order tensor of the dynamics (hess_body): it depends on the
         // iterate only, not on lambda or the regularisation, so every candidate of every round shares it
         const double* T = hess + (size_t)t * L::hess_stride * B + b;
+        constexpr int R = M::kRotVar;
+        static_for<sym_size(M::NV)>([&](auto E) {
+          constexpr int e = E;
+          constexpr int p = SymTable<M::NV>().i[e], q = SymTable<M::NV>().j[e];
+          if constexpr (p != R && q != R) {
+            constexpr int er = sym_idx(L::hess_red(p), L::hess_red(q), L::hess_nvj);
+            double acc = 0.0;
 #pragma unroll
-        for (int e = 0; e < sym_size(M::NV); ++e) {
-          double acc = 0.0;
-#pragma unroll
-          for (int i = 0; i < M::NXH; ++i) acc += lam[i] * T[(size_t)(i * sym_size(M::NV) + e) * B];
-          hxx[e] = acc;
+            for (int i = 0; i < M::NXH; ++i) acc += lam[i] * T[(size_t)(i * L::hess_row + er) * B];
+            hxx[e] = acc;
+          }
+        });
+        if constexpr (R >= 0) {
+          // entries with the heading phi (models.cuh kRotVar): (x' - x, y' - y) = R(phi) w with w independent of phi, so
+          // d/dphi (x' - x) = -(y' - y), d/dphi (y' - y) = x' - x and every mixed derivative is the same rotation of the
+          // first-order expansion; the other rows do not depend on phi
+          const double dx = traj[((size_t)(t + 1) * NX + 0) * B + b] - traj[((size_t)t * NX + 0) * B + b];
+          const double dy = traj[((size_t)(t + 1) * NX + 1) * B + b] - traj[((size_t)t * NX + 1) * B + b];
+          static_for<M::NV>([&](auto Wv) {
+            constexpr int w = Wv;
+            constexpr int e = sym_idx(w < R ? w : R, w < R ? R : w, M::NV);
+            if constexpr (w == R) {
+              hxx[e] = lam[0] * (-dx) + lam[1] * (-dy);
+            } else {
+              double gx = 0.0, gy = 0.0;   // d x' / d w, d y' / d w from the packed first-order expansion
+              static_for<NX>([&](auto C) {
+                constexpr int c = C;
+                if constexpr (M::sv(c) == w) {
+                  if constexpr (M::Nm(0, c)) gx = bl.N[0][c];
+                  if constexpr (M::Nm(1, c)) gy = bl.N[1][c];
+                }
+              });
+              static_for<NU>([&](auto Kc) {
+                constexpr int k = Kc;
+                if constexpr (M::uv(k) == w) {
+                  if constexpr (M::Bm(0, k)) gx = bl.B[0][k];
+                  if constexpr (M::Bm(1, k)) gy = bl.B[1][k];
+                }
+              });
+              hxx[e] = lam[0] * (-gy) + lam[1] * gx;
+            }
+          });
         }
       } else {
         // ... recomputed here by second-order jets (stand-alone ilqc_backward)

@@ -5,6 +5,8 @@
 // loop on the CPU so that the container without a GPU can check the arithmetic against the golden
 // vectors (tests/hostsim).  The host simulator is never part of libilqc_b200.so.
 #pragma once
+#include <cstdlib>
+#include <cstring>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
@@ -91,6 +93,26 @@ constexpr int kBlock = ILQC_BLOCK;
 #define ILQC_LB_ROLL 8
 #endif
 
+// launches of at most this many candidates use the warp-cooperative backward pass (coop.cuh)
+#ifndef ILQC_COOP_MAX_DEFAULT
+#define ILQC_COOP_MAX_DEFAULT 0
+#endif
+// engine tuning knobs (ilqc_set_tuning; initial values from the environment: ILQC_COOP_MAX, ILQC_FEED_SMALL)
+struct Tuning {
+  long long coop_max, feed_small;
+};
+inline Tuning tuning_defaults() {
+  Tuning x;
+  const char* e = getenv("ILQC_COOP_MAX");
+  x.coop_max = e ? atoll(e) : (long long)ILQC_COOP_MAX_DEFAULT;
+  e = getenv("ILQC_FEED_SMALL");
+  x.feed_small = e ? atoll(e) : 0LL;
+  return x;
+}
+inline Tuning& tuning() {
+  static Tuning t = tuning_defaults();
+  return t;
+}
 // internal flag or-ed into the backward mode: the slots map to (nearly) consecutive problems (all problems
 // active, candidates of a problem adjacent) -> the shared-memory operand feed pays off
 #define ILQC_BWD_DENSE_HINT 0x100

@@ -2,6 +2,7 @@
 // the test-only host simulator.  Each kernel is a thread-per-slot wrapper around a body of bodies.cuh.
 #include "launch.cuh"
 #include "bodies.cuh"
+#include "coop.cuh"
 
 #ifndef ILQC_MODEL_INST
 #error "define ILQC_MODEL_INST"
@@ -270,11 +271,23 @@ int Launch<ILQC_MODEL_INST>::backward(int mode, const ilqc_model_desc& m, int B,
   mode &= 0xf;
 #define ILQC_BWD_ARGS m, B, n_slots, prob, oslot, n_oslots, reg_ctrl, reg_state, lin, traj, cmd, hess, gains, jcst, feasible, bad_dir
   if (mode == ILQC_BWD_LINQUAD) {
+#if !defined(ILQC_HOSTSIM)
+    if constexpr (MI::NX == 8) {
+      // small (latency-bound) launches: 8 lanes per candidate (coop.cuh); identical results.  ILQC_COOP_MAX=<slots> tunes
+      // the switch-over (0 = never); measured in profiles/r02_tuning_small_rounds.txt
+      if ((long long)n_slots <= tuning().coop_max) {
+        constexpr int CPB = ILQC_COOP_BLOCK / 8;
+        backward_coop_kernel<MI, ILQC_BWD_LINQUAD><<<(n_slots + CPB - 1) / CPB, ILQC_COOP_BLOCK, 0, st>>>(
+            m, B, n_slots, prob, oslot, n_oslots, reg_ctrl, reg_state, lin, gains, jcst, feasible, bad_dir);
+        ++::ilqc::launch_counter();
+        return ILQC_LAUNCH_OK();
+      }
+    }
+#endif
     if constexpr (kBwdAsyncFeed<MI>) {
       // (ILQC_FEED_SMALL=<slots>: tuning knob - also stage the operands of launches of at most that many slots, which are
       //  latency-bound whatever their access pattern; measured in profiles/r02_tuning_small_rounds.txt)
-      static const long long feed_small = [] { const char* e = getenv("ILQC_FEED_SMALL"); return e ? atoll(e) : 0LL; }();
-      if ((dense && (long long)n_slots <= 5LL * B) || (long long)n_slots <= feed_small) {
+      if ((dense && (long long)n_slots <= 5LL * B) || (long long)n_slots <= tuning().feed_small) {
         ILQC_LAUNCH_SMEM((backward_kernel<MI, ILQC_BWD_LINQUAD, true, false>), n_slots, kBlock, kBwdSmemBytes<MI>, st, ILQC_BWD_ARGS);
         return ILQC_LAUNCH_OK();
       }

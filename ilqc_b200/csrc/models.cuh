@@ -1108,8 +1108,13 @@ struct Layout {
   static constexpr int oN = 0, oB = oN + nN, oq = oB + nB, oQ = oq + M::NU, op = oQ + M::NU, oP = op + np;
   static constexpr int stride = oP + nP;
   static constexpr int gain_stride = M::NU * M::NX + M::NU;
-  // second-order tensor of the dynamics: packed Hessians (over the NV jet variables) of the first NXH state rows
-  static constexpr int hess_stride = M::NXH * sym_size(M::NV);
+  // second-order tensor of the dynamics: packed Hessians of the first NXH state rows over the jet variables WITHOUT the
+  // heading (M::kRotVar): rows >= 2 do not depend on it and the heading entries of rows 0, 1 are rotations of the
+  // first-order expansion (bodies.cuh backward_body), so 6 x 15 instead of 6 x 21 doubles per step for the bicycle car
+  static constexpr int hess_nvj = M::kRotVar >= 0 ? M::NV - 1 : M::NV;
+  static constexpr int hess_row = sym_size(hess_nvj);
+  static constexpr int hess_stride = M::NXH * hess_row;
+  static constexpr int hess_red(int v) { return (v < 0 || v == M::kRotVar) ? -1 : ((M::kRotVar >= 0 && v > M::kRotVar) ? v - 1 : v); }
   // masks of the second-order path: Hessian of lambda^T phi lives on the jet variables
   static constexpr Mask<M::NX, M::NX> hxx() {
     Mask<M::NX, M::NX> k;

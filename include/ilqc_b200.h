@@ -243,6 +243,12 @@ int ilqc_from_soa(const double* src, double* dst, int B, int n, void* stream);
 int ilqc_profile_enable(int enable);
 int ilqc_profile_read(double* ms, int64_t* launches, int64_t* units, int n);
 
+/* Engine tuning knobs (no effect on results): "coop_max" = launches of the linear-quadratic backward pass with at most
+ * this many candidates use the warp-cooperative kernel (8 lanes per candidate, csrc/coop.cuh; identical gains),
+ * "feed_small" = ... the cp.async operand feed.  A negative value restores the default.  Returns ILQC_E_ARG for an unknown name.  (Engine-side only: the
+ * reference has no counterpart; its backward pass is envs/backward.py:6-57.) */
+int ilqc_set_tuning(const char* name, long long value);
+
 /* Number of kernels launched by this library since the last reset (all entry points, bookkeeping included). */
 long long ilqc_launch_count(int reset);
 

@@ -333,3 +333,36 @@ def test_headline_rows_inside_full_batch(cuda_engine):
         if not noisy:
             assert err[p, -1] < 1e-6, (p, err[p])
     assert sum(f == 21 for f in first) >= len(rows) // 2
+
+
+def test_coop_backward_identical_to_thread_per_candidate(cuda_engine):
+    """Warp-cooperative backward pass (csrc/coop.cuh, 8 lanes per candidate) against the thread-per-candidate kernel on
+    the bicycle model: identical gains, model decrease and feasibility for 300 candidates of 60 seeded problems (ragged
+    last block), so results do not depend on which kernel a line-search round uses.  Then a whole solve with the
+    cooperative kernel on every small round against the default solve."""
+    from bench import make_batch
+    eng = cuda_engine
+    env, x0, w = make_batch(60, 99)
+    g = torch.Generator().manual_seed(5)
+    cmd = 0.3 * torch.randn(60, env.horizon, env.dim_ctrl, generator=g, dtype=torch.float64)
+    ex = eng.linearize(env, x0, cmd, weights=w)
+    reg = (10.0 ** torch.linspace(-3, 6, 5, dtype=torch.float64)).reshape(1, 5).repeat(60, 1)
+    set_t = lambda v: _check_rc(eng.lib.ilqc_set_tuning(b"coop_max", v))
+    try:
+        set_t(0)
+        a = eng.backward(ex, 0, reg, L=5)
+        set_t(1 << 40)
+        b = eng.backward(ex, 0, reg, L=5)
+        assert torch.equal(a["gains"], b["gains"]) and torch.equal(a["jcst"], b["jcst"]) and torch.equal(a["feasible"], b["feasible"])
+        assert torch.isfinite(a["gains"]).all() and float(a["gains"].abs().max()) > 0
+        set_t(0)
+        r0 = eng.solve(env, "ddp_linquad_reg", 6, x0=x0, weights=w, record_trips=True)
+        set_t(1 << 40)
+        r1 = eng.solve(env, "ddp_linquad_reg", 6, x0=x0, weights=w, record_trips=True)
+        assert torch.equal(r0.cost, r1.cost) and torch.equal(r0.cmd, r1.cmd) and torch.equal(r0.ls_trips, r1.ls_trips)
+    finally:
+        _check_rc(eng.lib.ilqc_set_tuning(b"coop_max", -1))
+
+
+def _check_rc(rc):
+    assert rc == 0, rc
