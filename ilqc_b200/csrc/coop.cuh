@@ -329,7 +329,7 @@ backward_coop_kernel(ilqc_model_desc m, int B, int n_slots_active, const int32_t
 #pragma unroll
     for (int c = 0; c < NX; ++c) {
       double acc = Jr[c];
-      if (Pslot[c] >= 0) acc += Prow[c];   // (entries outside the stored pattern are skipped, as in riccati.cuh phase2)
+      if (Pslot[c] >= 0 || c == i) acc += Prow[c];   // (stored pattern + the diagonal, which carries reg_state: riccati.cuh phase2)
 #pragma unroll
       for (int u = 0; u < NU; ++u) acc += G[u] * Ks[u * NX + c];
       Jr[c] = acc;

@@ -254,7 +254,8 @@ struct Bell {
         constexpr int c = C;
         if constexpr (c >= i) {
           double acc = J[sym_idx(i, c, NX)];
-          if constexpr (Pat::Pm(i, c)) acc += P[i][c];
+          // (the diagonal also outside the stored pattern: it carries reg_state, backward.py:35 / :105)
+          if constexpr (Pat::Pm(i, c) || i == c) acc += P[i][c];
 #pragma unroll
           for (int u = 0; u < NU; ++u) acc += G[u][i] * K[u][c];
           J[sym_idx(i, c, NX)] = acc;

@@ -269,6 +269,13 @@ def check_random_config_vs_oracle(eng, seed, tol=1e-9):
         errs[mode + "_rol"] = relerr(d[0, 0], orc.roll_out_lin(steps, gains, 0.6).detach().numpy())
         d, _, _ = eng.rollout(lin, _lib.ROLL_EXACT, one(0.6), bw)
         errs[mode + "_roe"] = relerr(d[0, 0], orc.roll_out_exact(oenv, traj, gains, cmd, 0.6).detach().numpy())
+    # state regularisation (reg_state of lin_quad_backward / quad_backward, backward.py:35, :105): added to EVERY diagonal
+    # entry of the state-cost Hessian, also outside the model's stored sparsity pattern
+    for mode, mid in (("linquad", _lib.BWD_LINQUAD), ("ddp", _lib.BWD_QUAD_DDP)):
+        gains, jcst, feas = orc.backward(steps, 0.7, reg_state=0.3, mode=mode)
+        bw = eng.backward(lin, mid, one(0.7), reg_state=0.3)
+        errs[mode + "_regstate_K"] = relerr(bw["K"][0, 0], torch.stack([K for K, _ in gains]).detach().numpy())
+        errs[mode + "_regstate_jcst"] = abs(float(bw["jcst"][0, 0]) - float(jcst)) / (abs(float(jcst)) + 1e-300)
     # two solver iterations from these controls with a second- and a first-order algorithm (the solver contracts the
     # stored dynamics-Hessian tensor, eng.backward above recomputes it: both paths are compared with the oracle)
     for algo in (["ddp_quad_reg", "classic_quad_reg"][seed % 2], ["ddp_linquad_reg", "classic_linquad_dir"][(seed // 2) % 2]):
