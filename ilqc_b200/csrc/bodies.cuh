@@ -349,11 +349,32 @@ ILQC_HD void hess_body(const ilqc_model_desc& m, int b, int B, int t, const doub
 // backward pass (MODE = ILQC_BWD_*).  slot s serves problem b with regularisation reg_ctrl.
 // gains record per step: [K row-major NU x NX | k NU], layout [t][gain_stride][n_slots]
 // ----------------------------------------------------------------------------------------------------
-template <class M, int MODE, bool TENSOR, class Feed>
+// Feed of the stored dynamics-Hessian tensor into the second-order backward passes: step t contracts the
+// Layout<M>::hess_stride doubles of (problem, t) with its costate.
+//   DirectTensor: plain global loads at the point of use.  (A cp.async feed through shared memory - the thread's rows of
+//   step t-1 copied while step t computes, [hess_stride][block] doubles - was measured SLOWER on a B200: 3.01 ms against
+//   2.51 ms for the full first round; the 4 candidates of a problem copy from equal addresses and 8-byte cp.async
+//   requests of equal addresses serialise in the LSU, profiles/r02_tuning_small_rounds.txt.)
+struct DirectTensor {
+  const double* hess_b;  // hess + b
+  size_t B;
+  int stride;
+  const double* cur = nullptr;
+  ILQC_HD void prefetch(int) {}
+  ILQC_HD void acquire(int t) { cur = hess_b + (size_t)t * stride * B; }
+  ILQC_HD double operator()(int idx) const { return cur[(size_t)idx * B]; }
+};
+struct NoTensor {
+  ILQC_HD void prefetch(int) {}
+  ILQC_HD void acquire(int) {}
+  ILQC_HD double operator()(int) const { return 0.0; }
+};
+
+template <class M, int MODE, bool TENSOR, class Feed, class TFeed>
 ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, int B, double reg_ctrl,
                            double reg_state, const double* __restrict__ lin, const double* __restrict__ traj,
                            const double* __restrict__ cmd, const double* __restrict__ hess, double* __restrict__ gains,
-                           double* __restrict__ jcst_out, int32_t* __restrict__ feas_out, int bad_dir, Feed& feed) {
+                           double* __restrict__ jcst_out, int32_t* __restrict__ feas_out, int bad_dir, Feed& feed, TFeed& tfeed) {
   constexpr int NX = M::NX, NU = M::NU;
   constexpr bool QUAD = (MODE != ILQC_BWD_LINQUAD);
   using L = Layout<M>;
@@ -383,6 +404,7 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
   for (int i = 0; i < NX; ++i) lam[i] = j[i];
   double jcst = 0.0;
   feed.prefetch(H - 1);
+  if constexpr (TENSOR) tfeed.prefetch(H - 1);
   for (int t = H - 1; t >= 0; --t) {
     if (t > 0) feed.prefetch(t - 1);
     feed.acquire(t, t > 0);
@@ -403,7 +425,7 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
       if constexpr (TENSOR) {
         // contraction of the stored second-order tensor of the dynamics (hess_body): it depends on the
         // iterate only, not on lambda or the regularisation, so every candidate of every round shares it
-        const double* T = hess + (size_t)t * L::hess_stride * B + b;
+        tfeed.acquire(t);
         constexpr int R = M::kRotVar;
         static_for<sym_size(M::NV)>([&](auto E) {
           constexpr int e = E;
@@ -412,10 +434,11 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
             constexpr int er = sym_idx(L::hess_red(p), L::hess_red(q), L::hess_nvj);
             double acc = 0.0;
 #pragma unroll
-            for (int i = 0; i < M::NXH; ++i) acc += lam[i] * T[(size_t)(i * L::hess_row + er) * B];
+            for (int i = 0; i < M::NXH; ++i) acc += lam[i] * tfeed(i * L::hess_row + er);
             hxx[e] = acc;
           }
         });
+        if (t > 0) tfeed.prefetch(t - 1);   // (the buffer is free: every entry of step t has been read)
         if constexpr (R >= 0) {
           // entries with the heading phi (models.cuh kRotVar): (x' - x, y' - y) = R(phi) w with w independent of phi, so
           // d/dphi (x' - x) = -(y' - y), d/dphi (y' - y) = x' - x and every mixed derivative is the same rotation of the

@@ -53,12 +53,14 @@ ILQC_GLOBAL_LB(ILQC_LB_BWD) backward_kernel(ilqc_model_desc m, int B, int n_thre
   if constexpr (ASYNC) {
     extern __shared__ double ilqc_bwd_smem[];
     AsyncFeed<M> feed{lin + b, (size_t)B, ilqc_bwd_smem + threadIdx.x};
-    backward_body<M, MODE, TENSOR>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, hess, gains, jcst, feasible, bad_dir, feed);
+    NoTensor nt;
+    backward_body<M, MODE, TENSOR>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, hess, gains, jcst, feasible, bad_dir, feed, nt);
     return;
   }
 #endif
   DirectFeed<M> feed{lin + b, (size_t)B};
-  backward_body<M, MODE, TENSOR>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, hess, gains, jcst, feasible, bad_dir, feed);
+  DirectTensor tf{TENSOR ? hess + b : nullptr, (size_t)B, Layout<M>::hess_stride};
+  backward_body<M, MODE, TENSOR>(m, os, n_oslots, b, B, reg_ctrl[os], reg_state, lin, traj, cmd, hess, gains, jcst, feasible, bad_dir, feed, tf);
 }
 
 template <class M, int KIND>
