@@ -13,7 +13,8 @@ sys.path.insert(0, ROOT)
 from ilqc_b200 import build as b  # noqa: E402
 
 VARIANTS = {
-    "nofm": ["-DILQC_FASTMATH=0"],
+    "hg2": ["-DILQC_HESS_GROUPS=2"],
+    "hg4": ["-DILQC_HESS_GROUPS=4"],
 }
 
 
