@@ -659,13 +659,21 @@ ILQC_HD void rollout_body(const ilqc_model_desc& m, int s, int n_slots, int b, i
     }
     double xn[NX], q[NU], Qd[NU];
     M::template step<double>(m, x, u, xn);
+    // reference state that closes the step (dx = x_{t+1} - xbar_{t+1}), requested before the cost is evaluated so that its
+    // HBM latency hides behind the ~300 instructions of the cost (ncu source page, round 2: the subtraction below was the
+    // instruction with the most stall samples of the kernel, all long_scoreboard)
+    double xr[KIND == ILQC_ROLL_EXACT ? NX : 1];
+    if constexpr (KIND == ILQC_ROLL_EXACT) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xr[i] = traj[((size_t)(t + 1) * NX + i) * B + b];
+    }
     const double cs = M::template state_cost<double>(m, w, xn, t0 + t + 1);
     const double c = cs + M::ctrl_cost(m, u, q, Qd);
     tot = tot + c;
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
       x[i] = xn[i];
-      if constexpr (KIND == ILQC_ROLL_EXACT) dx[i] = xn[i] - traj[((size_t)(t + 1) * NX + i) * B + b];
+      if constexpr (KIND == ILQC_ROLL_EXACT) dx[i] = xn[i] - xr[i];
     }
   }
   newval[s] = tot;
