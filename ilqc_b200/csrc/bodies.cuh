@@ -231,12 +231,44 @@ ILQC_HD void load_state_cost(double (&p)[M::NX], double (&P)[M::NX][M::NX], cons
 //               255-register limit with 8 warps per SM, so nothing else can cover the HBM latency of the
 //               ~50 dependent-free loads per step (ncu before: 3.6 of 6.5 stall cycles per issue were
 //               long_scoreboard at 47 % of the HBM peak).
+#ifndef ILQC_BWD_PREFETCH
+#define ILQC_BWD_PREFETCH 2   // 0 off, 1 prefetch.global.L1, 2 prefetch.global.L2
+#endif
 template <class M>
 struct DirectFeed {
   const double* lin_b;  // lin + b
   size_t B;
   int t_cur = 0;
-  ILQC_HD void prefetch(int) {}
+  ILQC_HD void prefetch(int t) {
+#if ILQC_BWD_PREFETCH && defined(__CUDA_ARCH__)
+    // pull chunk(t) into L2 one step ahead (no registers, no shared memory): the gathered rounds spent 57 % of their stall
+    // samples in long_scoreboard at the first uses of N, B and of P, p (ncu source page, round 2); backward class
+    // 52.4 -> 50.1 ms per solve (profiles/r02_tuning_small_rounds.txt; .L1 and .L2 measured equal)
+    using L = Layout<M>;
+    const double* rt = lin_b + (size_t)t * L::stride * B;
+#pragma unroll
+    for (int c = 0; c < L::op; ++c) {
+#if ILQC_BWD_PREFETCH == 1
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(rt + (size_t)c * B));
+#else
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rt + (size_t)c * B));
+#endif
+    }
+    if (t > 0) {
+      const double* rp = rt - (size_t)L::stride * B;
+#pragma unroll
+      for (int c = L::op; c < L::stride; ++c) {
+#if ILQC_BWD_PREFETCH == 1
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + (size_t)c * B));
+#else
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (size_t)c * B));
+#endif
+      }
+    }
+#else
+    (void)t;
+#endif
+  }
   ILQC_HD void acquire(int t, bool) { t_cur = t; }
   ILQC_HD GlobalRec dyn() const { return GlobalRec{lin_b + (size_t)t_cur * Layout<M>::stride * B, B}; }
   ILQC_HD GlobalRec cost() const { return GlobalRec{lin_b + (size_t)(t_cur - 1) * Layout<M>::stride * B, B}; }
@@ -355,12 +387,22 @@ ILQC_HD void hess_body(const ilqc_model_desc& m, int b, int B, int t, const doub
 //   step t-1 copied while step t computes, [hess_stride][block] doubles - was measured SLOWER on a B200: 3.01 ms against
 //   2.51 ms for the full first round; the 4 candidates of a problem copy from equal addresses and 8-byte cp.async
 //   requests of equal addresses serialise in the LSU, profiles/r02_tuning_small_rounds.txt.)
+#ifndef ILQC_TENSOR_PREFETCH
+#define ILQC_TENSOR_PREFETCH 0
+#endif
 struct DirectTensor {
   const double* hess_b;  // hess + b
   size_t B;
   int stride;
   const double* cur = nullptr;
-  ILQC_HD void prefetch(int) {}
+  ILQC_HD void prefetch(int t) {
+#if ILQC_TENSOR_PREFETCH && defined(__CUDA_ARCH__)
+    const double* nx = hess_b + (size_t)t * stride * B;
+    for (int c = 0; c < stride; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)c * B));
+#else
+    (void)t;
+#endif
+  }
   ILQC_HD void acquire(int t) { cur = hess_b + (size_t)t * stride * B; }
   ILQC_HD double operator()(int idx) const { return cur[(size_t)idx * B]; }
 };
@@ -540,23 +582,21 @@ ILQC_HD void backward_body(const ilqc_model_desc& m, int s, int n_slots, int b, 
 #pragma unroll
       for (int i = 0; i < NX; ++i) lam_next[i] += bl.p[i];
     }
+    // (P + state block of the dynamics Hessian) + reg_state on the diagonal, applied where phase 2 uses P (riccati.cuh)
     if constexpr (!QUAD) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) bl.P[i][i] += reg_state;
+      bl.reg_diag = reg_state;
     } else {
-      if (t > 0) {  // P gets the state block of the dynamics Hessian and reg_state only for t>0 (backward.py:102-108)
-        static_for<NX>([&](auto I) {
-          constexpr int i = I;
-          if constexpr (M::sv(i) >= 0) {
-            static_for<NX>([&](auto Jc) {
-              constexpr int c = Jc;
-              if constexpr (c >= i && M::sv(c) >= 0) bl.P[i][c] += hxx[sym_idx(M::sv(i), M::sv(c), M::NV)];
-            });
-          }
-        });
-#pragma unroll
-        for (int i = 0; i < NX; ++i) bl.P[i][i] += reg_state;
-      }
+      // P gets the state block of the dynamics Hessian and reg_state only for t>0 (backward.py:102-108)
+      bl.reg_diag = t > 0 ? reg_state : 0.0;
+      static_for<NX>([&](auto I) {
+        constexpr int i = I;
+        if constexpr (M::sv(i) >= 0) {
+          static_for<NX>([&](auto Jc) {
+            constexpr int c = Jc;
+            if constexpr (c >= i && M::sv(c) >= 0) bl.Padd[i][c] = t > 0 ? hxx[sym_idx(M::sv(i), M::sv(c), M::NV)] : 0.0;
+          });
+        }
+      });
     }
     const double rest = bl.phase2(J, j);
     if constexpr (M::kPassivePRow >= 0) {

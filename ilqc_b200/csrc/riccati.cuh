@@ -31,6 +31,8 @@ struct PatOf {
   static constexpr auto Rm = Layout<M>::hxu();
   // Q: diagonal cost Hessian (+ full symmetric block on the jet controls when QUAD)
   static constexpr bool Qm(int u, int v) { return u == v || (QUAD_ && Layout<M>::huu()(u < v ? u : v, u < v ? v : u)); }
+  // entries of P that receive the state block of the dynamics Hessian (Bell::Padd)
+  static constexpr bool padd(int i, int c) { return QUAD_ && Layout<M>::hxx()(i, c); }
 };
 template <int NX_, int NU_, bool HAS_R>
 struct DensePat {
@@ -42,6 +44,7 @@ struct DensePat {
   static constexpr auto Pm = upper_of(full_mask<NX_, NX_>());
   static constexpr auto Rm = full_mask<NX_, NU_>();
   static constexpr bool Qm(int, int) { return true; }
+  static constexpr bool padd(int, int) { return false; }
 };
 
 template <class Pat>
@@ -57,6 +60,12 @@ struct Bell {
   double Q[NU][NU];  // upper triangle
   double q[NU];
   double R[NX][NU];
+  // added to P at its point of use in phase 2, in this order: (P + Padd) + reg_diag on the diagonal.  Kept apart from P
+  // so that nothing touches the freshly loaded P, p before the LU factorisation has been issued: an early
+  // `P[i][i] += reg_state` made the warp wait for the load right there (18 % of the stall samples of the gathered
+  // rounds, ncu source page round 2) instead of behind the three divisions of the LU.
+  double Padd[NX][NX];  // upper triangle, entries Pat::padd only (state block of the dynamics Hessian)
+  double reg_diag = 0.0;
   // intermediates carried from phase1 to phase2
   double G[NU][NX];
   double Hm[NU][NU];
@@ -255,7 +264,12 @@ struct Bell {
         if constexpr (c >= i) {
           double acc = J[sym_idx(i, c, NX)];
           // (the diagonal also outside the stored pattern: it carries reg_state, backward.py:35 / :105)
-          if constexpr (Pat::Pm(i, c) || i == c) acc += P[i][c];
+          if constexpr (Pat::Pm(i, c) || i == c) {
+            double pv = P[i][c];
+            if constexpr (Pat::padd(i, c)) pv += Padd[i][c];
+            if constexpr (i == c) pv += reg_diag;
+            acc += pv;
+          }
 #pragma unroll
           for (int u = 0; u < NU; ++u) acc += G[u][i] * K[u][c];
           J[sym_idx(i, c, NX)] = acc;

@@ -13,8 +13,7 @@ sys.path.insert(0, ROOT)
 from ilqc_b200 import build as b  # noqa: E402
 
 VARIANTS = {
-    "hg2": ["-DILQC_HESS_GROUPS=2"],
-    "hg4": ["-DILQC_HESS_GROUPS=4"],
+    "tpf": ["-DILQC_TENSOR_PREFETCH=1"],
 }
 
 
