@@ -387,22 +387,12 @@ ILQC_HD void hess_body(const ilqc_model_desc& m, int b, int B, int t, const doub
 //   step t-1 copied while step t computes, [hess_stride][block] doubles - was measured SLOWER on a B200: 3.01 ms against
 //   2.51 ms for the full first round; the 4 candidates of a problem copy from equal addresses and 8-byte cp.async
 //   requests of equal addresses serialise in the LSU, profiles/r02_tuning_small_rounds.txt.)
-#ifndef ILQC_TENSOR_PREFETCH
-#define ILQC_TENSOR_PREFETCH 0
-#endif
 struct DirectTensor {
   const double* hess_b;  // hess + b
   size_t B;
   int stride;
   const double* cur = nullptr;
-  ILQC_HD void prefetch(int t) {
-#if ILQC_TENSOR_PREFETCH && defined(__CUDA_ARCH__)
-    const double* nx = hess_b + (size_t)t * stride * B;
-    for (int c = 0; c < stride; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)c * B));
-#else
-    (void)t;
-#endif
-  }
+  ILQC_HD void prefetch(int) {}   // (prefetch.global.L2 of the next step's 90 rows: measured slower, 47.5 -> 53.4 ms per solve)
   ILQC_HD void acquire(int t) { cur = hess_b + (size_t)t * stride * B; }
   ILQC_HD double operator()(int idx) const { return cur[(size_t)idx * B]; }
 };
