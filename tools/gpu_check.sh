@@ -1,11 +1,9 @@
 #!/bin/bash
-# GPU box: smoke + gpu tests + short bench.  Outputs under gpurun_out/.
-set -x
+# GPU box: smoke + gpu tests + bench line (what the driver runs at round end).  Outputs under gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu_info.txt 2>&1
-nproc >> gpurun_out/gpu_info.txt
-timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log; tail -1 gpurun_out/smoke.log
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
-tail -15 gpurun_out/pytest_gpu.log
-timeout 900 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_short.json 2> gpurun_out/bench_short.err; echo "bench rc=$?"
-cat gpurun_out/bench_short.json; tail -5 gpurun_out/bench_short.err
+tail -3 gpurun_out/pytest_gpu.log
+timeout 1200 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"
+head -c 500 gpurun_out/bench_default.json; echo
